@@ -1,0 +1,238 @@
+#!/usr/bin/env python
+"""Build tests/golden/ from the reference checkout (run in the build container only).
+
+Reads /root/reference (never shipped, never read at test time on the GPU box), checks the oracle
+against EVERY golden vector the reference holds for the hot path, and writes compact fixtures:
+
+  tests/golden/pool.npz        content-addressed uint64 arrays (inputs: ciphertexts, KSKs,
+                               encoder outputs, kernel-level inputs)
+  tests/golden/manifest.json   programs, which pool array feeds what, and the sha256 of every
+                               expected output polynomial (+ which polys are all-'x')
+  tests/golden/isram/*.mem     the four microcode kernels (the R-type instruction streams that are
+                               the path's input format)
+  tests/golden/decode/*.json   sequencer decode goldens (instruction words + 17 expected fields)
+
+Expected outputs are stored as hashes, not data: a mismatch is diagnosed per polynomial, and the
+full reference dumps stay in the reference checkout.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import shutil
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+
+REF = os.environ.get("ALOHA_REFERENCE", "/root/reference")
+OUT = os.path.join(ROOT, "tests", "golden")
+N = O.N_TV
+
+# case3.txt is shipped; the other two programs are inferred and replay bit-exact.
+CASE3 = open(os.path.join(
+    REF, "vivado_prj/top_noaxilite.srcs/sources_1/imports/sim/model_run/case3.txt")).read()
+PROGRAMS = {
+    "case0_4_4": "\n".join([
+        "10000000,00000000,00000000", "70000100,00000002,00000000", "30000200,00000000,00000000",
+        "30000280,00000000,00010000", "50000300,00000000,00000200", "50000400,00000100,00000280",
+        "60000500,00000300,00000400", "20000500,00000000,00000000"]),
+    "case1_8_8": "\n".join(CASE3.split()[:12] + [
+        "70000300,00000004,00000300", "60000300,00000200,00000300", "20000300,00000000,00000000"]),
+    "case2_16_16": "\n".join(CASE3.split()),
+}
+KSK_STEPS = {"case0_4_4": [2], "case1_8_8": [2, 4], "case2_16_16": [2, 8]}
+
+
+def read_dump(path):
+    with open(path) as f:
+        lines = f.read().split()
+    mask = np.array([ln != "x" for ln in lines])
+    data = np.array([int(ln) if ln != "x" else 0 for ln in lines], dtype=np.uint64)
+    return data, mask
+
+
+def poly_hashes(data: np.ndarray, mask: np.ndarray, n: int = N):
+    """sha256 per polynomial; an all-'x' polynomial hashes to the string 'x'."""
+    out = []
+    for p in range(len(data) // n):
+        d, m = data[p * n:(p + 1) * n], mask[p * n:(p + 1) * n]
+        if not m.any():
+            out.append("x")
+        else:
+            assert m.all(), "partially written polynomial in a golden dump"
+            out.append(hashlib.sha256(np.ascontiguousarray(d).tobytes()).hexdigest())
+    return out
+
+
+class Pool:
+    def __init__(self):
+        self.arrays = {}
+
+    def add(self, a: np.ndarray) -> str:
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        key = "a" + hashlib.sha1(a.tobytes()).hexdigest()[:16]
+        self.arrays.setdefault(key, a)
+        return key
+
+
+def load_microcode(model):
+    d = os.path.join(REF, "sim/vp/isram_file_generator")
+    for name, pc in (("encode_post", 0), ("mul_plain", 64), ("hom_add", 160), ("keyswitch", 256)):
+        model.load_isram(O.parse_mem_words(open(os.path.join(d, name + ".mem")).read()), pc)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    pool = Pool()
+    manifest = {"n": N, "cases": {}, "kernels": [], "moduli": [[O.Q0, O.PSI0], [O.Q1, O.PSI1],
+                                                                [O.Q2, O.PSI2]]}
+    checked = 0
+
+    # ---- microcode + decode goldens -------------------------------------------------------
+    os.makedirs(os.path.join(OUT, "isram"), exist_ok=True)
+    for name in ("encode_post", "mul_plain", "hom_add", "keyswitch"):
+        shutil.copyfile(os.path.join(REF, "sim/vp/isram_file_generator", name + ".mem"),
+                        os.path.join(OUT, "isram", name + ".mem"))
+        os.chmod(os.path.join(OUT, "isram", name + ".mem"), 0o644)
+    os.makedirs(os.path.join(OUT, "decode"), exist_ok=True)
+    for mem, gold in (("add_inst", "homo_add"), ("mul_inst", "mul_plain"),
+                      ("inst_issue_test", "inst_issue_test")):
+        words = open(os.path.join(REF, "sim/vp/sequncer", mem + ".mem")).read().split()
+        rows = [ln.strip() for ln in
+                open(os.path.join(REF, "sim/vp/sequncer/golden", gold + ".txt")) if ln.strip()]
+        json.dump({"source": f"sim/vp/sequncer/{mem}.mem + golden/{gold}.txt",
+                   "words": words[:len(rows)], "fields": rows},
+                  open(os.path.join(OUT, "decode", gold + ".json"), "w"), indent=0)
+
+    # ---- full-system replays: every rtl_result dump -------------------------------------
+    for case, prog in PROGRAMS.items():
+        tv = os.path.join(REF, "tv", case)
+        ops = O.parse_program(prog)
+        model = O.GoldenModel()
+        load_microcode(model)
+        entry = {"program": prog.split("\n"), "ksk": {}, "loads": {}, "encoder": {}, "dumps": {}}
+        for j, step in enumerate(KSK_STEPS[case]):
+            ksk, _ = read_dump(os.path.join(tv, f"ksk_step{step}.txt"))
+            row = (O.clog2(step) - 1) * N * 12 // O.LANES
+            model.dma_ksk_h2d(row, ksk)
+            entry["ksk"][str(row)] = pool.add(ksk)
+        dram = np.zeros(64 * 1024 * 1024 // 8, dtype=np.uint64)
+        enc = {}
+        for i, op in enumerate(ops):
+            if op.kind == "load_cipher":
+                ct, m = read_dump(os.path.join(tv, "rtl_result", f"inst_{i}_out.txt"))
+                assert m.all()
+                base = (O.DRAM_VP_BASE + op.dram_addr) // 8
+                dram[base:base + 4 * N] = ct
+                entry["loads"][str(i)] = pool.add(ct)
+            elif op.kind == "encode":
+                d, m = read_dump(os.path.join(tv, "rtl_result", f"inst_{i}_0_out.txt"))
+                assert m[:2 * N].all()
+                enc[i] = d[:2 * N].copy()
+                entry["encoder"][str(i)] = pool.add(enc[i])
+        seen = set()
+        for i, sub, data, wr in O.replay(model, ops, dram, enc):
+            name = f"inst_{i}_out.txt" if sub is None else f"inst_{i}_{sub}_out.txt"
+            g, gm = read_dump(os.path.join(tv, "rtl_result", name))
+            assert (gm == wr).all(), f"{case}/{name}: x-mask differs"
+            assert (g[gm] == data[gm]).all(), f"{case}/{name}: data differs"
+            entry["dumps"][name[:-4]] = poly_hashes(g, gm)
+            seen.add(name)
+            checked += 1
+        shipped = set(os.listdir(os.path.join(tv, "rtl_result")))
+        assert seen == shipped, (case, shipped ^ seen)
+        manifest["cases"][case] = entry
+        print(f"{case}: {len(seen)} dumps bit-exact")
+
+    # case3_expected_result.txt == case2 inst_28 (top_noaxilite_tb.sv:663-683)
+    exp, m = read_dump(os.path.join(
+        REF, "vivado_prj/top_noaxilite.srcs/sources_1/new/case3_expected_result.txt"))
+    assert poly_hashes(exp, m) == manifest["cases"]["case2_16_16"]["dumps"]["inst_28_out"]
+    checked += 1
+
+    # ---- kernel-level software-model vectors: check all, ship a subset ---------------------
+    ship = {("case0_4_4", 1), ("case0_4_4", 4), ("case0_4_4", 6),
+            ("case1_8_8", 1), ("case1_8_8", 2), ("case1_8_8", 12)}
+    for case in PROGRAMS:
+        tv = os.path.join(REF, "tv", case)
+        files = os.listdir(tv)
+        kids = sorted({int(f.split("_")[0][6:]) for f in files if f.startswith("kernel")})
+        model = O.GoldenModel()
+        load_microcode(model)
+        ksks = {}
+        for step in KSK_STEPS[case]:
+            ksk, _ = read_dump(os.path.join(tv, f"ksk_step{step}.txt"))
+            row = (O.clog2(step) - 1) * N * 12 // O.LANES
+            model.dma_ksk_h2d(row, ksk)
+            ksks[step] = (row, ksk)
+        for k in kids:
+            mine = [f for f in files if f.startswith(f"kernel{k}_")]
+            rec = None
+            if f"kernel{k}_ct_after_rotate.txt" in mine:
+                ct, _ = read_dump(os.path.join(tv, f"kernel{k}_ct_before_rotate.txt"))
+                want, _ = read_dump(os.path.join(tv, f"kernel{k}_ct_after_rotate.txt"))
+                hit = None
+                for step, (row, _) in ksks.items():  # the file does not name its step: try each key
+                    model.dma_mem_h2d(0, ct)
+                    model.run_vp(O.ISRAM_KEYSWITCH, 0, 0, 512, row, pow(3, step, 2 * N))
+                    if (model.dma_mem_d2h(512, 4 * N) == want).all():
+                        hit = step
+                        break
+                assert hit is not None, f"{case} kernel{k} rotate: no KSK reproduces it"
+                rec = {"op": "rotate", "step": hit, "ksk_row": ksks[hit][0], "ksk": ksks[hit][1],
+                       "src0": ct, "want": want}
+            elif f"kernel{k}_ct_after_mulplain.txt" in mine:
+                ct, _ = read_dump(os.path.join(tv, f"kernel{k}_ct_before_mulplain.txt"))
+                pt, _ = read_dump(os.path.join(tv, f"kernel{k}_pt_before_mulplain.txt"))
+                want, _ = read_dump(os.path.join(tv, f"kernel{k}_ct_after_mulplain.txt"))
+                model.dma_mem_h2d(0, ct)
+                model.dma_mem_h2d(256, pt)
+                model.run_vp(O.ISRAM_MUL_PLAIN, 0, 256, 512)
+                assert (model.dma_mem_d2h(512, 4 * N) == want).all(), f"{case} kernel{k} mulplain"
+                rec = {"op": "mul_plain", "src0": ct, "src1": pt, "want": want}
+            elif f"kernel{k}_ct_after_homadd.txt" in mine:
+                c1, _ = read_dump(os.path.join(tv, f"kernel{k}_ct_before_homaddct1.txt"))
+                c2, _ = read_dump(os.path.join(tv, f"kernel{k}_ct_before_homaddct2.txt"))
+                want, _ = read_dump(os.path.join(tv, f"kernel{k}_ct_after_homadd.txt"))
+                model.dma_mem_h2d(0, c1)
+                model.dma_mem_h2d(256, c2)
+                model.run_vp(O.ISRAM_HOM_ADD, 0, 256, 512)
+                assert (model.dma_mem_d2h(512, 4 * N) == want).all(), f"{case} kernel{k} homadd"
+                rec = {"op": "hom_add", "src0": c1, "src1": c2, "want": want}
+            elif f"kernel{k}_pt_after_encode_fft_mod.txt" in mine:
+                pt, _ = read_dump(os.path.join(tv, f"kernel{k}_pt_after_encode_fft_mod.txt"))
+                want, _ = read_dump(os.path.join(tv, f"kernel{k}_pt_after_encode.txt"))
+                model.dma_mem_h2d(0, pt)
+                model.run_vp(O.ISRAM_ENCODE_POST, 0, 0, 512)
+                assert (model.dma_mem_d2h(512, 2 * N) == want).all(), f"{case} kernel{k} encode_post"
+                rec = {"op": "encode_post", "src0": pt, "want": want}
+            if rec is None:
+                continue  # case0's encode kernels ship no coefficient-domain input
+            checked += 1
+            if (case, k) in ship:
+                item = {"case": case, "kernel": k, "op": rec["op"],
+                        "want": poly_hashes(rec["want"], np.ones(len(rec["want"]), bool))}
+                for key in ("src0", "src1", "ksk"):
+                    if key in rec:
+                        item[key] = pool.add(rec[key])
+                for key in ("step", "ksk_row"):
+                    if key in rec:
+                        item[key] = rec[key]
+                manifest["kernels"].append(item)
+        print(f"{case}: kernel-level vectors bit-exact")
+
+    np.savez_compressed(os.path.join(OUT, "pool.npz"), **pool.arrays)
+    manifest["vectors_checked"] = checked
+    json.dump(manifest, open(os.path.join(OUT, "manifest.json"), "w"), indent=1)
+    size = os.path.getsize(os.path.join(OUT, "pool.npz"))
+    print(f"checked {checked} reference vectors; pool.npz = {size / 1e6:.1f} MB "
+          f"({len(pool.arrays)} arrays)")
+
+
+if __name__ == "__main__":
+    main()
