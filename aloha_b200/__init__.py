@@ -1,0 +1,319 @@
+"""aloha_b200 -- B200-native execution engine for ALOHA's leveled-FHE vector datapath.
+
+Python face of the C-ABI in include/aloha_b200.h (ctypes; no torch types cross the boundary).
+`Engine` mirrors the reference testbench's host tasks one to one
+(sim/top/top_noaxilite_tb.sv: run_vp :396-417, run_load_cipher :450-472, run_store_cipher :474-496,
+load_ksk :372-394) and `HostDriver` its op-list replay (:249-298, :596-638).
+
+There is no CPU fallback: importing works anywhere (so the build check can run), but creating an
+Engine without the CUDA library or without an sm_100 device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+__all__ = ["Engine", "HostDriver", "AlohaError", "load_library", "decode", "REFERENCE_MODULI",
+           "LANES", "VLMAX_BITS", "SPM_ROWS", "KSK_ROWS"]
+
+LANES = 128
+VLMAX_BITS = 524288          # src/vp/include/vp_defines.vh:24
+SPM_ROWS = 16384             # src/mem_buf/spm.sv:47-178
+KSK_ROWS = 9216              # src/mem_buf/ksk_mem.sv:12-16
+# sim/vp/tf_rom_generator/tf_rom_generator.sv:75-77  (q, psi)
+REFERENCE_MODULI = ((576460825317867521, 3825716582911), (576460924102115329, 79932510954937),
+                    (576462951330889729, 101017252977188))
+
+F_NO_BATCH, F_NO_ALIAS, F_GRAPHS = 1, 2, 4
+
+_ERRORS = {-1: "E_ARG", -2: "E_RANGE", -3: "E_OPCODE", -4: "E_STATE", -5: "E_ILLEGAL", -6: "E_NOBREAK",
+           -7: "E_UNDEFINED", -8: "E_CUDA", -9: "E_NOMEM"}
+
+
+class AlohaError(RuntimeError):
+    def __init__(self, code: int, what: str, detail: str = ""):
+        self.code = code
+        self.name = _ERRORS.get(code, str(code))
+        super().__init__(f"{what}: {self.name} {detail}".strip())
+
+
+class _Cfg(C.Structure):
+    _fields_ = [("vlmax_bits", C.c_uint64), ("spm_rows", C.c_uint32), ("ksk_rows", C.c_uint32),
+                ("device", C.c_int32), ("flags", C.c_uint32), ("pool_buffers", C.c_uint32),
+                ("l2_chunk_bytes", C.c_uint64)]
+
+
+class VpArgs(C.Structure):
+    _fields_ = [("src0", C.c_uint32), ("src1", C.c_uint32), ("rslt", C.c_uint32),
+                ("ksk_ptr", C.c_uint32), ("step", C.c_uint32)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("kernel_launches", "instructions", "plans_built",
+                                          "plans_reused", "copies_elided", "copies_emitted",
+                                          "limb_ntts")]
+
+
+EXPORTS = ["aloha_create", "aloha_destroy", "aloha_strerror", "aloha_last_error", "aloha_load_isram",
+           "aloha_load_tf_rom", "aloha_dma_mem_h2d", "aloha_dma_mem_d2h", "aloha_dma_ksk_h2d",
+           "aloha_spm_written", "aloha_run_vp", "aloha_run_vp_batch", "aloha_sync",
+           "aloha_spm_device_ptr", "aloha_ksk_device_ptr", "aloha_spm_mark_written", "aloha_set_stream",
+           "aloha_get_stats", "aloha_get_csr", "aloha_decode", "aloha_host_create",
+           "aloha_host_destroy", "aloha_host_num_ops", "aloha_host_dram_write", "aloha_host_dram_read",
+           "aloha_host_set_encoder_output", "aloha_host_run_op", "aloha_write_dump_text"]
+
+_lib = None
+
+
+def load_library(rebuild: bool = False) -> C.CDLL:
+    """dlopen aloha_b200/libaloha_b200.so (building it with nvcc first if it is missing/stale)."""
+    global _lib
+    if _lib is not None and not rebuild:
+        return _lib
+    path = _build.LIB
+    if rebuild or not os.path.exists(path) or (_build.stale() and os.path.exists(_build.NVCC)):
+        path = _build.build(force=rebuild)
+    if not os.path.exists(path):
+        raise AlohaError(-8, "load_library", f"{path} is missing and cannot be built (no nvcc); "
+                         "the engine has no CPU fallback")
+    L = C.CDLL(path)
+    u64, u32, vp = C.c_uint64, C.c_uint32, C.c_void_p
+    p64, p8 = C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)
+    sig = {
+        "aloha_create": (C.c_int, [C.POINTER(_Cfg), C.POINTER(vp)]),
+        "aloha_destroy": (None, [vp]),
+        "aloha_strerror": (C.c_char_p, [C.c_int]),
+        "aloha_last_error": (C.c_char_p, [vp]),
+        "aloha_load_isram": (C.c_int, [vp, p8, u32, u32]),
+        "aloha_load_tf_rom": (C.c_int, [vp, p64, p64, u32]),
+        "aloha_dma_mem_h2d": (C.c_int, [vp, u32, vp, u64]),
+        "aloha_dma_mem_d2h": (C.c_int, [vp, vp, u32, u64]),
+        "aloha_dma_ksk_h2d": (C.c_int, [vp, u32, vp, u64]),
+        "aloha_spm_written": (C.c_int, [vp, u32, u64, p8]),
+        "aloha_run_vp": (C.c_int, [vp, u32, u32, u32, u32, u32, u32]),
+        "aloha_run_vp_batch": (C.c_int, [vp, u32, u32, C.POINTER(VpArgs)]),
+        "aloha_sync": (C.c_int, [vp]),
+        "aloha_spm_device_ptr": (C.c_int, [vp, u32, C.POINTER(vp)]),
+        "aloha_ksk_device_ptr": (C.c_int, [vp, u32, C.POINTER(vp)]),
+        "aloha_spm_mark_written": (C.c_int, [vp, u32, u32]),
+        "aloha_set_stream": (C.c_int, [vp, vp]),
+        "aloha_get_stats": (C.c_int, [vp, C.POINTER(_Stats)]),
+        "aloha_get_csr": (C.c_int, [vp, p64, p64, p64]),
+        "aloha_decode": (C.c_int, [p8, u64, p64]),
+        "aloha_host_create": (C.c_int, [vp, C.c_char_p, u64, u32, C.POINTER(vp)]),
+        "aloha_host_destroy": (None, [vp]),
+        "aloha_host_num_ops": (C.c_int, [vp]),
+        "aloha_host_dram_write": (C.c_int, [vp, u64, vp, u64]),
+        "aloha_host_dram_read": (C.c_int, [vp, u64, vp, u64]),
+        "aloha_host_set_encoder_output": (C.c_int, [vp, u32, p64, u64]),
+        "aloha_host_run_op": (C.c_int, [vp, u32, p64, p8, p64, p8, C.POINTER(C.c_int)]),
+        "aloha_write_dump_text": (C.c_int, [C.c_char_p, p64, p8, u64]),
+    }
+    assert sorted(sig) == sorted(EXPORTS)
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)   # raises AttributeError if the library lacks a declared symbol
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _p64(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def _p8(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def decode(word12: bytes, csr_step: int = 0) -> list[int]:
+    """17 micro-op fields of one 96-bit instruction word (sim/vp/sequncer/seq_top_tb.sv:138-160)."""
+    w = np.frombuffer(bytes(word12), dtype=np.uint8).copy()
+    out = np.zeros(17, dtype=np.uint64)
+    rc = load_library().aloha_decode(_p8(w), csr_step, _p64(out))
+    if rc:
+        raise AlohaError(rc, "decode")
+    return [int(x) for x in out]
+
+
+class Engine:
+    """One ALOHA vector processor on one GPU: SPM, KSK memory, 32 vregs and CSRs live in HBM."""
+
+    def __init__(self, vlmax_bits=VLMAX_BITS, spm_rows=SPM_ROWS, ksk_rows=KSK_ROWS, device=0, flags=0,
+                 moduli=REFERENCE_MODULI, pool_buffers=0, l2_chunk_bytes=0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        self.nmax = vlmax_bits // 64
+        cfg = _Cfg(vlmax_bits, spm_rows, ksk_rows, device, flags, pool_buffers, l2_chunk_bytes)
+        rc = self.L.aloha_create(C.byref(cfg), C.byref(self.h))
+        if rc:
+            detail = self.L.aloha_last_error(self.h).decode() if self.h else ""
+            if self.h:
+                self.L.aloha_destroy(self.h)
+                self.h = None
+            raise AlohaError(rc, "aloha_create", detail)
+        if moduli:
+            self.load_tf_rom([m[0] for m in moduli], [m[1] for m in moduli])
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.aloha_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc: int, what: str):
+        if rc:
+            raise AlohaError(rc, what, self.L.aloha_last_error(self.h).decode())
+
+    # ---- provisioning
+    def load_isram(self, words: np.ndarray, at_pc: int):
+        words = np.ascontiguousarray(words, dtype=np.uint8)
+        assert words.ndim == 2 and words.shape[1] == 12
+        self._ck(self.L.aloha_load_isram(self.h, _p8(words), len(words), at_pc), "load_isram")
+
+    def load_tf_rom(self, q, psi):
+        q = np.array(q, dtype=np.uint64)
+        psi = np.array(psi, dtype=np.uint64)
+        self._ck(self.L.aloha_load_tf_rom(self.h, _p64(q), _p64(psi), len(q)), "load_tf_rom")
+
+    # ---- DMA
+    def dma_mem_h2d(self, spm_row: int, data):
+        if isinstance(data, np.ndarray):
+            data = np.ascontiguousarray(data, dtype=np.uint64)
+            ptr, nbytes = data.ctypes.data, data.nbytes
+        else:                      # (address, nbytes) of a pinned host buffer
+            ptr, nbytes = data
+        self._ck(self.L.aloha_dma_mem_h2d(self.h, spm_row, ptr, nbytes), "dma_mem_h2d")
+
+    def dma_mem_d2h(self, spm_row: int, nwords: int, out=None) -> np.ndarray:
+        if out is None:
+            out = np.empty(nwords, dtype=np.uint64)
+            ptr = out.ctypes.data
+        else:
+            ptr = out if isinstance(out, int) else out.ctypes.data
+        self._ck(self.L.aloha_dma_mem_d2h(self.h, ptr, spm_row, nwords * 8), "dma_mem_d2h")
+        return out
+
+    def dma_ksk_h2d(self, ksk_row: int, data: np.ndarray):
+        data = np.ascontiguousarray(data, dtype=np.uint64)
+        self._ck(self.L.aloha_dma_ksk_h2d(self.h, ksk_row, data.ctypes.data, data.nbytes), "dma_ksk_h2d")
+
+    def spm_written(self, spm_row: int, nwords: int) -> np.ndarray:
+        out = np.empty(nwords, dtype=np.uint8)
+        self._ck(self.L.aloha_spm_written(self.h, spm_row, nwords, _p8(out)), "spm_written")
+        return out.astype(bool)
+
+    # ---- execution
+    def run_vp(self, pc, src0=0, src1=0, rslt=0, ksk_ptr=0, step=0):
+        self._ck(self.L.aloha_run_vp(self.h, pc, src0, src1, rslt, ksk_ptr, step), f"run_vp(pc={pc})")
+
+    @staticmethod
+    def make_args(calls) -> "C.Array[VpArgs]":
+        """calls: iterable of (src0, src1, rslt, ksk_ptr, step)."""
+        calls = list(calls)
+        arr = (VpArgs * len(calls))()
+        for i, c in enumerate(calls):
+            arr[i] = VpArgs(*c)
+        return arr
+
+    def run_vp_batch(self, pc: int, args):
+        if not isinstance(args, C.Array):
+            args = self.make_args(args)
+        self._ck(self.L.aloha_run_vp_batch(self.h, pc, len(args), args), f"run_vp_batch(pc={pc})")
+
+    def sync(self):
+        self._ck(self.L.aloha_sync(self.h), "sync")
+
+    # ---- device-side access
+    def spm_device_ptr(self, spm_row: int) -> int:
+        p = C.c_void_p()
+        self._ck(self.L.aloha_spm_device_ptr(self.h, spm_row, C.byref(p)), "spm_device_ptr")
+        return p.value
+
+    def ksk_device_ptr(self, ksk_row: int) -> int:
+        p = C.c_void_p()
+        self._ck(self.L.aloha_ksk_device_ptr(self.h, ksk_row, C.byref(p)), "ksk_device_ptr")
+        return p.value
+
+    def spm_mark_written(self, spm_row: int, nrows: int):
+        self._ck(self.L.aloha_spm_mark_written(self.h, spm_row, nrows), "spm_mark_written")
+
+    def set_stream(self, cuda_stream: int | None):
+        self._ck(self.L.aloha_set_stream(self.h, cuda_stream), "set_stream")
+
+    def stats(self) -> dict:
+        s = _Stats()
+        self._ck(self.L.aloha_get_stats(self.h, C.byref(s)), "get_stats")
+        return {n: int(getattr(s, n)) for n, _ in _Stats._fields_}
+
+    def csr(self) -> tuple[int, int, int]:
+        vl, q, iq = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self.L.aloha_get_csr(self.h, C.byref(vl), C.byref(q), C.byref(iq)), "get_csr")
+        return vl.value, q.value, iq.value
+
+
+class HostDriver:
+    """The testbench's host program runner (PROGRAM file + DDR image -> per-op dumps)."""
+
+    def __init__(self, engine: Engine, program_text: str, n: int = 8192, dram_bytes: int = 64 << 20):
+        self.eng, self.n, self.L = engine, n, engine.L
+        self.h = C.c_void_p()
+        rc = self.L.aloha_host_create(engine.h, program_text.encode(), dram_bytes, n, C.byref(self.h))
+        if rc:
+            raise AlohaError(rc, "host_create")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.aloha_host_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __len__(self):
+        return self.L.aloha_host_num_ops(self.h)
+
+    def dram_write(self, byte_addr: int, data: np.ndarray):
+        data = np.ascontiguousarray(data)
+        rc = self.L.aloha_host_dram_write(self.h, byte_addr, data.ctypes.data, data.nbytes)
+        if rc:
+            raise AlohaError(rc, "dram_write")
+
+    def dram_read(self, byte_addr: int, nwords: int) -> np.ndarray:
+        out = np.empty(nwords, dtype=np.uint64)
+        rc = self.L.aloha_host_dram_read(self.h, byte_addr, out.ctypes.data, out.nbytes)
+        if rc:
+            raise AlohaError(rc, "dram_read")
+        return out
+
+    def set_encoder_output(self, op_index: int, data: np.ndarray):
+        data = np.ascontiguousarray(data, dtype=np.uint64)
+        rc = self.L.aloha_host_set_encoder_output(self.h, op_index, _p64(data), len(data))
+        if rc:
+            raise AlohaError(rc, "set_encoder_output")
+
+    def run_op(self, i: int):
+        """-> [(sub_id or None, data[4n], written[4n])] in the order the TB writes its dump files."""
+        w = 4 * self.n
+        dump, sub = np.empty(w, np.uint64), np.empty(w, np.uint64)
+        wr, swr = np.empty(w, np.uint8), np.empty(w, np.uint8)
+        has_sub = C.c_int(0)
+        rc = self.L.aloha_host_run_op(self.h, i, _p64(dump), _p8(wr), _p64(sub), _p8(swr), C.byref(has_sub))
+        if rc:
+            raise AlohaError(rc, f"host_run_op({i})", self.L.aloha_last_error(self.eng.h).decode())
+        out = []
+        if has_sub.value:
+            out.append((0, sub, swr.astype(bool)))
+        out.append((None, dump, wr.astype(bool)))
+        return out
+
+    @staticmethod
+    def write_dump_text(path: str, data: np.ndarray, written: np.ndarray):
+        data = np.ascontiguousarray(data, dtype=np.uint64)
+        wr = np.ascontiguousarray(written, dtype=np.uint8)
+        rc = load_library().aloha_write_dump_text(path.encode(), _p64(data), _p8(wr), len(data))
+        if rc:
+            raise AlohaError(rc, "write_dump_text")

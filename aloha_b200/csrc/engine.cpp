@@ -1,0 +1,839 @@
+// engine.cpp -- machine state, batcher (symbolic execution -> levelled launch plan), executor, C-ABI.
+// See engine.hpp for the execution model and include/aloha_b200.h for the boundary.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+using namespace alb;
+typedef unsigned __int128 u128;
+
+namespace {
+
+#define CU(call)                                                                        \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) {                                                        \
+            E->last_error = std::string(#call) + ": " + cudaGetErrorString(e_);         \
+            return ALOHA_E_CUDA;                                                        \
+        }                                                                               \
+    } while (0)
+
+int fail(aloha *E, int code, const std::string &msg) {
+    E->last_error = msg;
+    return code;
+}
+
+unsigned ilog2(u64 x) { unsigned l = 0; while ((1ull << l) < x) ++l; return l; }
+
+u64 powmod(u64 a, u64 e, u64 q) {
+    u64 r = 1 % q;
+    a %= q;
+    while (e) {
+        if (e & 1) r = (u64)((u128)r * a % q);
+        a = (u64)((u128)a * a % q);
+        e >>= 1;
+    }
+    return r;
+}
+u64 bitrev(u64 x, unsigned bits) {
+    u64 r = 0;
+    for (unsigned i = 0; i < bits; ++i) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+}
+Tw shoup(u64 w, u64 q) {
+    Tw t;
+    t.w = w;
+    t.wp = (u64)(((u128)w << 64) / q);
+    return t;
+}
+
+// ------------------------------------------------------------------------------ twiddle tables
+// Index j holds root^bitrev(j, logN) -- the reference ROM's order
+// (sim/vp/tf_rom_generator/tf_rom_generator.sv:28-30,61-63,111,147-148).
+int get_tables(aloha *E, int mod, unsigned logn, const TwTable **out) {
+    auto key = std::make_pair(mod, logn);
+    auto it = E->tw_tables.find(key);
+    if (it != E->tw_tables.end()) { *out = &it->second; return ALOHA_OK; }
+    const u64 q = E->mod_q[mod], n = 1ull << logn;
+    if (q <= (1ull << 59) || q >= (1ull << 60))
+        return fail(E, ALOHA_E_STATE, "transform modulus must be a 60-bit prime (mod_width = 60, vxu_lane.sv:539)");
+    if ((q - 1) % (2 * n)) return fail(E, ALOHA_E_STATE, "2N does not divide q-1");
+    const u64 psi = powmod(E->mod_psi[mod], E->nmax / n, q);
+    if (powmod(psi, n, q) != q - 1) return fail(E, ALOHA_E_STATE, "psi is not a primitive 2N-th root of unity");
+    const u64 ipsi = powmod(psi, q - 2, q);
+    std::vector<Tw> fwd(n), inv(n);
+    u64 cf = 1, ci = 1;
+    for (u64 e = 0; e < n; ++e) {
+        const u64 j = bitrev(e, logn);
+        fwd[j] = shoup(cf, q);
+        inv[j] = shoup(ci, q);
+        cf = (u64)((u128)cf * psi % q);
+        ci = (u64)((u128)ci * ipsi % q);
+    }
+    TwTable t;
+    CU(cudaMalloc(&t.fwd, n * sizeof(Tw)));
+    CU(cudaMalloc(&t.inv, n * sizeof(Tw)));
+    CU(cudaMemcpy(t.fwd, fwd.data(), n * sizeof(Tw), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t.inv, inv.data(), n * sizeof(Tw), cudaMemcpyHostToDevice));
+    const u64 ninv = powmod(n % q, q - 2, q);
+    const Tw a = shoup(ninv, q), b = shoup((u64)((u128)inv[1].w * ninv % q), q);
+    t.mc.q = q;
+    t.mc.ninv = a.w; t.mc.ninv_p = a.wp;
+    t.mc.wninv = b.w; t.mc.wninv_p = b.wp;
+    t.mc.mest = (u32)((((u128)1) << 91) / q);
+    *out = &(E->tw_tables[key] = t);
+    return ALOHA_OK;
+}
+
+void free_tables(aloha *E) {
+    for (auto &kv : E->tw_tables) { cudaFree(kv.second.fwd); cudaFree(kv.second.inv); }
+    E->tw_tables.clear();
+}
+void free_plans(aloha *E) {
+    for (auto &kv : E->plans) {
+        if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
+        cudaFree(kv.second.d_tables);
+    }
+    E->plans.clear();
+}
+
+inline bool overlap(const u64 *a, u64 an, const u64 *b, u64 bn) {
+    return a && b && a < b + bn && b < a + an;
+}
+
+// ------------------------------------------------------------------------------ batcher
+struct Builder {
+    aloha *E;
+    std::vector<VecOp> ops;
+    Loc loc[32];
+    u64 vl, q, iq;
+    int mod_idx;
+    std::deque<u32> free_bufs;
+    std::vector<int> producer;          // pool buffer -> index of the op that wrote it in this plan
+    std::vector<std::pair<u64, u64>> written;
+    u64 instructions = 0, limb_ntts = 0, elided = 0, emitted = 0;
+
+    explicit Builder(aloha *e) : E(e), vl(e->vl), q(e->q), iq(e->iq), mod_idx(e->mod_idx) {
+        std::vector<uint8_t> used(E->pool_count, 0);
+        for (int r = 0; r < 32; ++r) {
+            loc[r] = E->loc[r];
+            if (loc[r].space == SP_POOL) used[loc[r].off] = 1;
+        }
+        for (u32 b = 0; b < E->pool_count; ++b) if (!used[b]) free_bufs.push_back(b);
+        producer.assign(E->pool_count, -1);
+    }
+
+    u64 *ptr(const Loc &l) const { return E->ptr(l); }
+
+    int alloc(Loc *out, u64 n) {
+        if (free_bufs.empty()) return fail(E, ALOHA_E_NOMEM, "renaming pool exhausted");
+        out->space = SP_POOL;
+        out->off = free_bufs.front();
+        out->n = n;
+        free_bufs.pop_front();
+        producer[out->off] = -1;
+        return ALOHA_OK;
+    }
+    void release(const Loc &l) {
+        if (l.space == SP_POOL) { free_bufs.push_back((u32)l.off); producer[l.off] = -1; }
+    }
+    // vd gets a fresh value living at `nl`
+    void define(int vd, const Loc &nl) {
+        release(loc[vd]);
+        loc[vd] = nl;
+    }
+    void emit_copy(u64 *dst, const u64 *src, u64 n) {
+        VecOp o{};
+        o.kind = K_COPY;
+        o.n = (u32)n;
+        o.dst = dst;
+        o.a = src;
+        ops.push_back(o);
+        ++emitted;
+    }
+    // Something is about to overwrite words [off, off+n) of `space`: registers aliasing that range
+    // keep their value by moving to a pool buffer first (copy-on-write).
+    int cow(Space space, u64 off, u64 n, int except_reg, bool *moved = nullptr) {
+        for (int r = 0; r < 32; ++r) {
+            if (r == except_reg || loc[r].space != space) continue;
+            if (!(loc[r].off < off + n && off < loc[r].off + loc[r].n)) continue;
+            Loc nl;
+            int rc = alloc(&nl, loc[r].n);
+            if (rc) return rc;
+            emit_copy(ptr(nl), ptr(loc[r]), loc[r].n);
+            producer[nl.off] = (int)ops.size() - 1;
+            loc[r] = nl;
+            if (moved) *moved = true;
+        }
+        return ALOHA_OK;
+    }
+
+    int read_loc(int reg, u64 n, const u64 **out) {
+        if (reg < 0) return fail(E, ALOHA_E_OPCODE, "operand port disabled");
+        const Loc &l = loc[reg];
+        if (l.space == SP_UNDEF)
+            return fail(E, ALOHA_E_UNDEFINED,
+                        "v" + std::to_string(reg) + " read while undefined (never written, or clobbered by VNTT/VINTT)");
+        if (l.n < n) return fail(E, ALOHA_E_UNDEFINED, "v" + std::to_string(reg) + " holds fewer words than vl");
+        *out = ptr(l);
+        return ALOHA_OK;
+    }
+
+    // vp_top_full.sv:105-117 + addr_gen.v:44
+    int resolve_mem(u64 imm, bool is_load, const aloha_vp_args &a, u64 rows, Space *space, u64 *word_off) {
+        const unsigned sel = (unsigned)(imm >> 48);
+        const u64 off = (imm >> 10) & 0xffff;
+        if (off + rows > 0x10000) return fail(E, ALOHA_E_RANGE, "VLE/VSE row offset wraps the 16-bit row field");
+        const bool ksk = is_load && sel == 15;
+        const u64 base = ksk ? a.ksk_ptr : sel == 0 ? a.src0 : sel == 1 ? a.src1 : sel == 2 ? a.rslt : 0;
+        const u64 limit = ksk ? E->cfg.ksk_rows : E->cfg.spm_rows;
+        if (base + off + rows > limit) return fail(E, ALOHA_E_RANGE, "VLE/VSE rows outside SPM/KSK memory");
+        *space = ksk ? SP_KSK : SP_SPM;
+        *word_off = (base + off) * kLanes;
+        return ALOHA_OK;
+    }
+
+    int store(int vs, u64 word_off, u64 n) {
+        if (vs < 0) return fail(E, ALOHA_E_OPCODE, "VSE source port disabled");
+        if (loc[vs].space == SP_UNDEF) return fail(E, ALOHA_E_UNDEFINED, "VSE of undefined v" + std::to_string(vs));
+        if (loc[vs].n < n) return fail(E, ALOHA_E_UNDEFINED, "VSE of a register shorter than vl");
+        u64 *M = E->d_spm + word_off;
+        written.emplace_back(word_off, n);
+        if (loc[vs].space == SP_SPM && loc[vs].off == word_off) { ++elided; return ALOHA_OK; }  // already there
+        // the source itself may alias a partially overlapping SPM range: move it out first
+        if (loc[vs].space == SP_SPM && loc[vs].off < word_off + n && word_off < loc[vs].off + loc[vs].n) {
+            Loc nl;
+            int rc = alloc(&nl, loc[vs].n);
+            if (rc) return rc;
+            emit_copy(ptr(nl), ptr(loc[vs]), loc[vs].n);
+            producer[nl.off] = (int)ops.size() - 1;
+            loc[vs] = nl;
+        }
+        // copy-on-write copies are appended AFTER the producer in program order, so a store that
+        // needed one cannot be forwarded back into the producer
+        bool moved = false;
+        int rc = cow(SP_SPM, word_off, n, vs, &moved);
+        if (rc) return rc;
+        const bool alias_ok = !(E->cfg.flags & ALOHA_F_NO_ALIAS) && !moved;
+        if (alias_ok && loc[vs].space == SP_POOL && loc[vs].n == n && producer[loc[vs].off] >= 0) {
+            const int p = producer[loc[vs].off];
+            const u64 *X = ptr(loc[vs]);
+            VecOp &po = ops[p];
+            bool ok = true;
+            // the producer may read M only as an exact in-place operand of an index-preserving kernel
+            const bool inplace_safe = po.kind == K_EW || po.kind == K_NTT || po.kind == K_INTT || po.kind == K_COPY;
+            for (const u64 *s : {po.a, po.b})
+                if (overlap(s, po.n, M, n) && !(inplace_safe && s == M)) ok = false;
+            // nothing between the producer and here may touch M
+            for (size_t j = p + 1; ok && j < ops.size(); ++j) {
+                const VecOp &o = ops[j];
+                if (overlap(o.dst, o.n, M, n) || overlap(o.a, o.n, M, n) || overlap(o.b, o.n, M, n)) ok = false;
+            }
+            if (ok) {
+                for (size_t j = p + 1; j < ops.size(); ++j) {
+                    if (ops[j].a == X) ops[j].a = M;
+                    if (ops[j].b == X) ops[j].b = M;
+                }
+                po.dst = M;
+                Loc nl;
+                nl.space = SP_SPM;
+                nl.off = word_off;
+                nl.n = n;
+                define(vs, nl);
+                ++elided;
+                return ALOHA_OK;
+            }
+        }
+        emit_copy(M, ptr(loc[vs]), n);
+        return ALOHA_OK;
+    }
+
+    int step(const Inst &in, const aloha_vp_args &a, bool *brk) {
+        ++instructions;
+        const MicroOp m = expand(in, a.step);
+        *brk = in.funct6 == F6_BREAK;
+        if (m.cfg == 1) {  // seq_top.v:417-429
+            const u64 n = m.scalar_cfg / 64;
+            if (m.scalar_cfg % 64 || n < 256 || (n & (n - 1)) || n > E->nmax)
+                return fail(E, ALOHA_E_STATE, "VSETVL: vl/64 must be a power of two in [256, vlmax/64]");
+            vl = m.scalar_cfg;
+            return ALOHA_OK;
+        }
+        if (m.cfg == 2) {  // vxu_top.sv:112-118
+            q = m.scalar_cfg;
+            mod_idx = -1;
+            for (size_t i = 0; i < E->mod_q.size(); ++i)
+                if (E->mod_q[i] == q) { mod_idx = (int)i; break; }
+            return ALOHA_OK;
+        }
+        if (m.cfg == 3) { iq = m.scalar_cfg; return ALOHA_OK; }
+        switch (in.funct6) {
+        case F6_BREAK: case F6_NOP: return ALOHA_OK;
+        case F6_FQMUL: case F6_FQADD: case F6_FQSUB: case F6_FQMOD: case F6_VCPY: case F6_VAUT:
+        case F6_VROLI: case F6_NTT: case F6_INTT: case F6_VLE: case F6_VSE: break;
+        default: return fail(E, ALOHA_E_OPCODE, "unknown funct6 " + std::to_string(in.funct6));
+        }
+        if ((in.funct6 == F6_FQMUL || in.funct6 == F6_FQADD) && in.funct3 > 1)
+            return fail(E, ALOHA_E_OPCODE, "unsupported funct3");
+        if (in.funct6 == F6_FQSUB && in.funct3 > 2) return fail(E, ALOHA_E_OPCODE, "unsupported funct3");
+        if (!vl) return fail(E, ALOHA_E_STATE, "vector op before VSETVL");
+        const u64 n = vl / 64, rows = n / kLanes;
+        const int r0 = port_reg(m.b0r, 0), r1 = port_reg(m.b1r, 1);
+        const int w0 = port_reg(m.b0w, 0), w1 = port_reg(m.b1w, 1);
+        const int wd = w0 >= 0 ? w0 : w1;
+        auto rd = [&](unsigned bit) { return ((m.muxo >> bit) & 1) ? r1 : r0; };
+
+        if (m.ls == 1) {
+            Space sp;
+            u64 off;
+            int rc = resolve_mem(m.scalar_ls, true, a, rows, &sp, &off);
+            if (rc) return rc;
+            if (wd < 0) return fail(E, ALOHA_E_OPCODE, "VLE without destination");
+            Loc nl;
+            if (E->cfg.flags & ALOHA_F_NO_ALIAS) {
+                rc = alloc(&nl, n);
+                if (rc) return rc;
+                emit_copy(ptr(nl), (sp == SP_KSK ? E->d_ksk : E->d_spm) + off, n);
+                producer[nl.off] = (int)ops.size() - 1;
+            } else {
+                nl.space = sp;
+                nl.off = off;
+                nl.n = n;
+                ++elided;
+            }
+            define(wd, nl);
+            return ALOHA_OK;
+        }
+        if (m.ls == 2) {
+            Space sp;
+            u64 off;
+            int rc = resolve_mem(m.scalar_ls, false, a, rows, &sp, &off);
+            if (rc) return rc;
+            return store(rd(0), off, n);
+        }
+        if (!q) return fail(E, ALOHA_E_STATE, "ALU op before VSETQ");
+        if (wd < 0) return fail(E, ALOHA_E_OPCODE, "no destination register");
+
+        VecOp o{};
+        o.n = (u32)n;
+        o.q = q;
+        o.iq = iq;
+        int src_reg = -1;
+        if (m.ntt == 2 || m.ntt == 3) {
+            src_reg = m.ntt == 2 ? rd(1) : rd(3);
+            if (src_reg == wd) return fail(E, ALOHA_E_ILLEGAL, "VNTT/VINTT with vd == vs1");
+            if (mod_idx < 0) return fail(E, ALOHA_E_STATE, "VNTT/VINTT under a modulus with no twiddle ROM (aloha_load_tf_rom)");
+            o.kind = m.ntt == 2 ? K_NTT : K_INTT;
+            o.mod = mod_idx;
+            int rc = read_loc(src_reg, n, &o.a);
+            if (rc) return rc;
+            const TwTable *t;
+            rc = get_tables(E, mod_idx, ilog2(n), &t);
+            if (rc) return rc;
+            ++limb_ntts;
+        } else if (m.iconn == 1 || m.iconn == 2) {
+            src_reg = rd(1);
+            if (src_reg == wd) return fail(E, ALOHA_E_ILLEGAL, "VAUT/VROLI with vd == vs1");
+            int rc = read_loc(src_reg, n, &o.a);
+            if (rc) return rc;
+            if (m.iconn == 1) {
+                o.kind = K_VAUT;
+                o.k = m.scalar_iconn & ((1ull << E->kbits) - 1);   // vxu_lane.sv:594 truncation
+                if (!(o.k & 1)) return fail(E, ALOHA_E_ILLEGAL, "VAUT with even k");
+                u64 inv = o.k;                                      // Newton: k^-1 mod 2^64
+                for (int i = 0; i < 6; ++i) inv *= 2 - o.k * inv;
+                o.kinv = inv & (n - 1);
+            } else {
+                o.kind = K_VROLI;
+                o.kinv = m.scalar_iconn & (n - 1);
+            }
+        } else {
+            o.kind = K_EW;
+            o.alu = (u32)m.alu;
+            const bool vv = o.alu == A_MULVV || o.alu == A_ADDVV || o.alu == A_SUBVV;
+            int rc = read_loc(rd(3), n, &o.a);
+            if (rc) return rc;
+            if (vv) {
+                rc = read_loc(rd(2), n, &o.b);
+                if (rc) return rc;
+            }
+            o.s = m.scalar_alu >= q ? m.scalar_alu - q : m.scalar_alu;   // modalu.sv:46
+        }
+        Loc nl;
+        int rc = alloc(&nl, n);
+        if (rc) return rc;
+        o.dst = ptr(nl);
+        ops.push_back(o);
+        producer[nl.off] = (int)ops.size() - 1;
+        define(wd, nl);
+        if ((o.kind == K_NTT || o.kind == K_INTT) && src_reg >= 0 && src_reg != wd) {
+            // The RTL ping-pongs through vs1 and leaves an intermediate stage there.
+            // This engine does not reproduce that content: the register becomes undefined.
+            release(loc[src_reg]);
+            loc[src_reg] = Loc{};
+        }
+        return ALOHA_OK;
+    }
+};
+
+// ASAP levels from true dependencies on address ranges.
+struct RangeState { u64 n; int last_write, last_read; };
+
+void assign_levels(std::vector<VecOp> &ops, bool sequential) {
+    if (sequential) {
+        for (size_t i = 0; i < ops.size(); ++i) ops[i].level = (int)i + 1;
+        return;
+    }
+    std::multimap<uintptr_t, RangeState> ranges;   // keyed by start address (bytes)
+    u64 maxlen = 0;
+    for (auto &o : ops) maxlen = std::max<u64>(maxlen, o.n);
+    auto scan = [&](const u64 *p, u64 n, bool want_readers) {
+        int lvl = 0;
+        if (!p) return lvl;
+        const uintptr_t lo = (uintptr_t)p, hi = lo + n * 8;
+        for (auto it = ranges.lower_bound(lo - std::min<uintptr_t>(lo, maxlen * 8)); it != ranges.end() && it->first < hi; ++it) {
+            if (it->first + it->second.n * 8 <= lo) continue;
+            lvl = std::max(lvl, it->second.last_write);
+            if (want_readers) lvl = std::max(lvl, it->second.last_read);
+        }
+        return lvl;
+    };
+    auto touch = [&](const u64 *p, u64 n, int level, bool is_write) {
+        if (!p) return;
+        auto range = ranges.equal_range((uintptr_t)p);
+        for (auto it = range.first; it != range.second; ++it) {
+            if (it->second.n == n) {
+                if (is_write) it->second.last_write = std::max(it->second.last_write, level);
+                else it->second.last_read = std::max(it->second.last_read, level);
+                return;
+            }
+        }
+        ranges.emplace((uintptr_t)p, RangeState{n, is_write ? level : 0, is_write ? 0 : level});
+    };
+    for (auto &o : ops) {
+        int lvl = std::max(scan(o.a, o.n, false), scan(o.b, o.n, false));
+        lvl = std::max(lvl, scan(o.dst, o.n, true));
+        o.level = lvl + 1;
+        touch(o.a, o.n, o.level, false);
+        touch(o.b, o.n, o.level, false);
+        touch(o.dst, o.n, o.level, true);
+    }
+}
+
+template <class T>
+size_t append(std::vector<uint8_t> &buf, const T &v) {
+    const size_t off = buf.size();
+    buf.resize(off + sizeof(T));
+    std::memcpy(buf.data() + off, &v, sizeof(T));
+    return off;
+}
+
+int compile_plan(aloha *E, Builder &B, Plan *plan) {
+    std::vector<VecOp> &ops = B.ops;
+    assign_levels(ops, E->cfg.flags & ALOHA_F_NO_BATCH);
+    std::vector<size_t> order(ops.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+        const VecOp &a = ops[x], &b = ops[y];
+        if (a.level != b.level) return a.level < b.level;
+        if (a.kind != b.kind) return a.kind < b.kind;
+        if (a.alu != b.alu) return a.alu < b.alu;
+        return a.n < b.n;
+    });
+    std::vector<uint8_t> tables;
+    const u64 chunk_bytes = E->cfg.l2_chunk_bytes ? E->cfg.l2_chunk_bytes : (32ull << 20);
+    size_t i = 0;
+    while (i < order.size()) {
+        const VecOp &h = ops[order[i]];
+        size_t j = i;
+        while (j < order.size() && ops[order[j]].level == h.level && ops[order[j]].kind == h.kind &&
+               ops[order[j]].alu == h.alu && ops[order[j]].n == h.n)
+            ++j;
+        // transforms: keep one chunk's src+dst footprint inside L2 between the two passes
+        size_t max_jobs = 65535;
+        if (h.kind == K_NTT || h.kind == K_INTT)
+            max_jobs = std::max<u64>(1, chunk_bytes / (2ull * h.n * 8));
+        while (tables.size() % 16) tables.push_back(0);
+        for (size_t c = i; c < j;) {
+            const size_t cnt = std::min(max_jobs, j - c);
+            Launch L{h.kind, h.alu, h.n, (u32)cnt, tables.size()};
+            for (size_t t = c; t < c + cnt; ++t) {
+                const VecOp &o = ops[order[t]];
+                switch (o.kind) {
+                case K_EW: append(tables, EwJob{o.dst, o.a, o.b, o.s, o.q, o.iq}); break;
+                case K_COPY: append(tables, CopyJob{o.dst, o.a}); break;
+                case K_VAUT:
+                case K_VROLI: append(tables, PermJob{o.dst, o.a, o.q, o.k, o.kinv}); break;
+                case K_NTT:
+                case K_INTT: {
+                    const TwTable *tw;
+                    int rc = get_tables(E, o.mod, ilog2(o.n), &tw);
+                    if (rc) return rc;
+                    NttJob nj{o.a, o.dst, o.kind == K_NTT ? tw->fwd : tw->inv, tw->mc};
+                    append(tables, nj);
+                    break;
+                }
+                }
+            }
+            plan->launches.push_back(L);
+            c += cnt;
+        }
+        i = j;
+    }
+    plan->table_bytes = tables.size();
+    if (!tables.empty()) {
+        CU(cudaMalloc(&plan->d_tables, tables.size()));
+        CU(cudaMemcpyAsync(plan->d_tables, tables.data(), tables.size(), cudaMemcpyHostToDevice, E->stream));
+        CU(cudaStreamSynchronize(E->stream));   // `tables` is a pageable temporary
+    }
+    plan->vl = B.vl; plan->q = B.q; plan->iq = B.iq; plan->mod_idx = B.mod_idx;
+    for (int r = 0; r < 32; ++r) plan->loc[r] = B.loc[r];
+    plan->written = B.written;
+    plan->instructions = B.instructions;
+    plan->limb_ntts = B.limb_ntts;
+    plan->elided = B.elided;
+    plan->emitted = B.emitted;
+    return ALOHA_OK;
+}
+
+int issue(aloha *E, const Plan &plan, u64 *launched) {
+    const uint8_t *base = (const uint8_t *)plan.d_tables;
+    const unsigned long long before = kernel_launch_count();
+    for (const Launch &L : plan.launches) {
+        const void *tab = base + L.table_off;
+        cudaError_t e = cudaSuccess;
+        switch (L.kind) {
+        case K_EW: e = launch_ew(L.alu, (const EwJob *)tab, L.njobs, L.n, E->stream); break;
+        case K_COPY: e = launch_copy((const CopyJob *)tab, L.njobs, L.n, E->stream); break;
+        case K_VAUT: e = launch_vaut((const PermJob *)tab, L.njobs, L.n, E->stream); break;
+        case K_VROLI: e = launch_vroli((const PermJob *)tab, L.njobs, L.n, E->stream); break;
+        case K_NTT: e = launch_ntt_forward((const NttJob *)tab, L.njobs, ilog2(L.n), E->stream); break;
+        case K_INTT: e = launch_ntt_inverse((const NttJob *)tab, L.njobs, ilog2(L.n), E->stream); break;
+        }
+        if (e != cudaSuccess) {
+            E->last_error = std::string("kernel launch: ") + cudaGetErrorString(e);
+            return ALOHA_E_CUDA;
+        }
+    }
+    *launched = kernel_launch_count() - before;
+    return ALOHA_OK;
+}
+
+int execute_plan(aloha *E, Plan &plan) {
+    u64 launched = 0;
+    if ((E->cfg.flags & ALOHA_F_GRAPHS) && !plan.launches.empty()) {
+        if (!plan.graph) {
+            cudaGraph_t g;
+            CU(cudaStreamBeginCapture(E->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = issue(E, plan, &launched);
+            cudaError_t ce = cudaStreamEndCapture(E->stream, &g);
+            if (rc) return rc;
+            CU(ce);
+            plan.kernel_launches = launched;
+            CU(cudaGraphInstantiate(&plan.graph, g, 0));
+            cudaGraphDestroy(g);
+        }
+        CU(cudaGraphLaunch(plan.graph, E->stream));
+        launched = plan.kernel_launches;
+    } else {
+        int rc = issue(E, plan, &launched);
+        if (rc) return rc;
+    }
+    E->stats.kernel_launches += launched;
+    return ALOHA_OK;
+}
+
+void mark_written(aloha *E, u64 word_off, u64 nwords) {
+    const u64 b0 = word_off / 8, b1 = (word_off + nwords + 7) / 8;
+    std::memset(E->written.data() + b0, 1, b1 - b0);
+}
+
+void commit(aloha *E, const Plan &plan) {
+    E->vl = plan.vl; E->q = plan.q; E->iq = plan.iq; E->mod_idx = plan.mod_idx;
+    for (int r = 0; r < 32; ++r) E->loc[r] = plan.loc[r];
+    for (auto &w : plan.written) mark_written(E, w.first, w.second);
+    E->stats.instructions += plan.instructions;
+    E->stats.limb_ntts += plan.limb_ntts;
+    E->stats.copies_elided += plan.elided;
+    E->stats.copies_emitted += plan.emitted;
+}
+
+std::string plan_key(const aloha *E, uint32_t pc, uint32_t count, const aloha_vp_args *args) {
+    std::string k;
+    auto put = [&](const void *p, size_t n) { k.append((const char *)p, n); };
+    put(&pc, 4); put(&count, 4);
+    put(args, sizeof(aloha_vp_args) * count);
+    put(&E->vl, 8); put(&E->q, 8); put(&E->iq, 8); put(&E->mod_idx, 4);
+    for (int r = 0; r < 32; ++r) { put(&E->loc[r].space, 1); put(&E->loc[r].off, 8); put(&E->loc[r].n, 8); }
+    put(&E->isram_version, 8); put(&E->tf_version, 8);
+    return k;
+}
+
+int run_batch(aloha *E, uint32_t pc, uint32_t count, const aloha_vp_args *args) {
+    if (!count) return ALOHA_OK;
+    const std::string key = plan_key(E, pc, count, args);
+    auto it = E->plans.find(key);
+    if (it == E->plans.end()) {
+        Builder B(E);
+        for (uint32_t c = 0; c < count; ++c) {
+            bool brk = false;
+            for (u64 at = pc; !brk; ++at) {
+                if (at >= kIramDepth) return fail(E, ALOHA_E_NOBREAK, "ran off the instruction ROM without BREAK");
+                const Inst in = parse_word(&E->isram[at * 12]);
+                int rc = B.step(in, args[c], &brk);
+                if (rc) return rc;
+            }
+        }
+        Plan plan;
+        int rc = compile_plan(E, B, &plan);
+        if (rc) { cudaFree(plan.d_tables); return rc; }
+        if (E->plans.size() >= 512) free_plans(E);
+        it = E->plans.emplace(key, std::move(plan)).first;
+        ++E->stats.plans_built;
+    } else {
+        ++E->stats.plans_reused;
+    }
+    int rc = execute_plan(E, it->second);
+    if (rc) return rc;
+    commit(E, it->second);
+    return ALOHA_OK;
+}
+
+// A host-side write into SPM words [off, off+n): registers aliasing the range move out first.
+int cow_for_host_write(aloha *E, u64 off, u64 n) {
+    bool any = false;
+    for (int r = 0; r < 32; ++r)
+        if (E->loc[r].space == SP_SPM && E->loc[r].off < off + n && off < E->loc[r].off + E->loc[r].n) any = true;
+    if (!any) return ALOHA_OK;
+    Builder B(E);
+    int rc = B.cow(SP_SPM, off, n, -1);
+    if (rc) return rc;
+    Plan plan;
+    rc = compile_plan(E, B, &plan);
+    if (!rc) rc = execute_plan(E, plan);
+    if (!rc) {
+        CU(cudaStreamSynchronize(E->stream));
+        commit(E, plan);
+    }
+    cudaFree(plan.d_tables);
+    return rc;
+}
+
+}  // namespace
+
+// ================================================================================== C-ABI
+extern "C" {
+
+const char *aloha_strerror(int code) {
+    switch (code) {
+    case ALOHA_OK: return "ok";
+    case ALOHA_E_ARG: return "bad argument";
+    case ALOHA_E_RANGE: return "address out of range";
+    case ALOHA_E_OPCODE: return "unknown or malformed instruction";
+    case ALOHA_E_STATE: return "machine not configured for this operation";
+    case ALOHA_E_ILLEGAL: return "instruction stream has no defined behaviour";
+    case ALOHA_E_NOBREAK: return "no BREAK before the end of the instruction ROM";
+    case ALOHA_E_UNDEFINED: return "read of an undefined vector register";
+    case ALOHA_E_CUDA: return "CUDA error";
+    case ALOHA_E_NOMEM: return "out of memory";
+    default: return "unknown error";
+    }
+}
+
+const char *aloha_last_error(const aloha_t *E) { return E ? E->last_error.c_str() : "null handle"; }
+
+int aloha_create(const aloha_cfg *cfg, aloha_t **out) {
+    if (!cfg || !out) return ALOHA_E_ARG;
+    const u64 nmax = cfg->vlmax_bits / 64;
+    if (cfg->vlmax_bits % 64 || nmax < 256 || nmax > 65536 || (nmax & (nmax - 1)) || !cfg->spm_rows) return ALOHA_E_ARG;
+    aloha *E = new aloha();
+    E->cfg = *cfg;
+    E->nmax = nmax;
+    E->kbits = ilog2(nmax);
+    E->device = cfg->device;
+    E->pool_count = cfg->pool_buffers ? cfg->pool_buffers : 64;
+    if (E->pool_count < 34) E->pool_count = 34;
+    *out = E;   // so the caller can read last_error on failure, then destroy
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device) {
+        E->last_error = "no CUDA device " + std::to_string(cfg->device) + " (this engine has no CPU fallback)";
+        return ALOHA_E_CUDA;
+    }
+    CU(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        E->last_error = "device is sm_" + std::to_string(prop.major * 10 + prop.minor) + "; kernels are built for sm_100a only";
+        return ALOHA_E_CUDA;
+    }
+    CU(cudaStreamCreateWithFlags(&E->own_stream, cudaStreamNonBlocking));
+    E->stream = E->own_stream;
+    E->spm_words = (u64)cfg->spm_rows * kLanes;
+    E->ksk_words = (u64)cfg->ksk_rows * kLanes;
+    CU(cudaMalloc(&E->d_spm, E->spm_words * 8));
+    CU(cudaMemsetAsync(E->d_spm, 0, E->spm_words * 8, E->stream));
+    if (E->ksk_words) {
+        CU(cudaMalloc(&E->d_ksk, E->ksk_words * 8));
+        CU(cudaMemsetAsync(E->d_ksk, 0, E->ksk_words * 8, E->stream));
+    }
+    CU(cudaMalloc(&E->d_pool, (u64)E->pool_count * nmax * 8));
+    E->isram.assign(kIramDepth * 12, 0);
+    E->written.assign((E->spm_words + 7) / 8, 0);
+    CU(cudaStreamSynchronize(E->stream));
+    return ALOHA_OK;
+}
+
+void aloha_destroy(aloha_t *E) {
+    if (!E) return;
+    if (E->own_stream) cudaStreamSynchronize(E->own_stream);
+    free_plans(E);
+    free_tables(E);
+    cudaFree(E->d_spm);
+    cudaFree(E->d_ksk);
+    cudaFree(E->d_pool);
+    if (E->own_stream) cudaStreamDestroy(E->own_stream);
+    delete E;
+}
+
+int aloha_load_isram(aloha_t *E, const uint8_t *words, uint32_t n, uint32_t at_pc) {
+    if (!E || !words) return ALOHA_E_ARG;
+    if ((u64)at_pc + n > kIramDepth) return fail(E, ALOHA_E_RANGE, "instruction ROM has 4096 entries");
+    std::memcpy(&E->isram[(size_t)at_pc * 12], words, (size_t)n * 12);
+    ++E->isram_version;
+    return ALOHA_OK;
+}
+
+int aloha_load_tf_rom(aloha_t *E, const uint64_t *q, const uint64_t *psi, uint32_t n) {
+    if (!E || !q || !psi) return ALOHA_E_ARG;
+    CU(cudaStreamSynchronize(E->stream));
+    free_tables(E);
+    E->mod_q.assign(q, q + n);
+    E->mod_psi.assign(psi, psi + n);
+    ++E->tf_version;
+    // re-resolve the current modulus against the new ROM set
+    E->mod_idx = -1;
+    for (size_t i = 0; i < E->mod_q.size(); ++i) if (E->mod_q[i] == E->q) { E->mod_idx = (int)i; break; }
+    return ALOHA_OK;
+}
+
+int aloha_dma_mem_h2d(aloha_t *E, uint32_t row, const uint64_t *src, uint64_t bytes) {
+    if (!E || !src || bytes % 64) return ALOHA_E_ARG;
+    const u64 off = (u64)row * kLanes, n = bytes / 8;
+    if (off + n > E->spm_words) return fail(E, ALOHA_E_RANGE, "DMA beyond SPM");
+    int rc = cow_for_host_write(E, off, n);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(E->d_spm + off, src, bytes, cudaMemcpyHostToDevice, E->stream));
+    mark_written(E, off, n);
+    return ALOHA_OK;
+}
+
+int aloha_dma_mem_d2h(aloha_t *E, uint64_t *dst, uint32_t row, uint64_t bytes) {
+    if (!E || !dst || bytes % 64) return ALOHA_E_ARG;
+    const u64 off = (u64)row * kLanes, n = bytes / 8;
+    if (off + n > E->spm_words) return fail(E, ALOHA_E_RANGE, "DMA beyond SPM");
+    CU(cudaMemcpyAsync(dst, E->d_spm + off, bytes, cudaMemcpyDeviceToHost, E->stream));
+    CU(cudaStreamSynchronize(E->stream));
+    return ALOHA_OK;
+}
+
+int aloha_dma_ksk_h2d(aloha_t *E, uint32_t row, const uint64_t *src, uint64_t bytes) {
+    if (!E || !src || bytes % 64) return ALOHA_E_ARG;
+    const u64 off = (u64)row * kLanes, n = bytes / 8;
+    if (off + n > E->ksk_words) return fail(E, ALOHA_E_RANGE, "DMA beyond KSK memory");
+    // registers aliasing KSK rows (VLE base 15) keep the OLD key: move them out first
+    bool any = false;
+    for (int r = 0; r < 32; ++r)
+        if (E->loc[r].space == SP_KSK && E->loc[r].off < off + n && off < E->loc[r].off + E->loc[r].n) any = true;
+    if (any) {
+        Builder B(E);
+        int rc = B.cow(SP_KSK, off, n, -1);
+        Plan plan;
+        if (!rc) rc = compile_plan(E, B, &plan);
+        if (!rc) rc = execute_plan(E, plan);
+        if (!rc) commit(E, plan);
+        cudaStreamSynchronize(E->stream);
+        cudaFree(plan.d_tables);
+        if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(E->d_ksk + off, src, bytes, cudaMemcpyHostToDevice, E->stream));
+    return ALOHA_OK;
+}
+
+int aloha_spm_written(aloha_t *E, uint32_t row, uint64_t nwords, uint8_t *out) {
+    if (!E || !out) return ALOHA_E_ARG;
+    const u64 off = (u64)row * kLanes;
+    if (off + nwords > E->spm_words) return fail(E, ALOHA_E_RANGE, "range beyond SPM");
+    for (u64 i = 0; i < nwords; ++i) out[i] = E->written[(off + i) / 8];
+    return ALOHA_OK;
+}
+
+int aloha_run_vp(aloha_t *E, uint32_t pc, uint32_t src0, uint32_t src1, uint32_t rslt, uint32_t ksk_ptr,
+                 uint32_t step) {
+    if (!E) return ALOHA_E_ARG;
+    const aloha_vp_args a{src0, src1, rslt, ksk_ptr, step};
+    return run_batch(E, pc, 1, &a);
+}
+
+int aloha_run_vp_batch(aloha_t *E, uint32_t pc, uint32_t count, const aloha_vp_args *args) {
+    if (!E || (count && !args)) return ALOHA_E_ARG;
+    return run_batch(E, pc, count, args);
+}
+
+int aloha_sync(aloha_t *E) {
+    if (!E) return ALOHA_E_ARG;
+    CU(cudaStreamSynchronize(E->stream));
+    return ALOHA_OK;
+}
+
+int aloha_spm_device_ptr(aloha_t *E, uint32_t row, void **p) {
+    if (!E || !p) return ALOHA_E_ARG;
+    if (row >= E->cfg.spm_rows) return fail(E, ALOHA_E_RANGE, "row beyond SPM");
+    *p = E->d_spm + (u64)row * kLanes;
+    return ALOHA_OK;
+}
+int aloha_ksk_device_ptr(aloha_t *E, uint32_t row, void **p) {
+    if (!E || !p) return ALOHA_E_ARG;
+    if (row >= E->cfg.ksk_rows) return fail(E, ALOHA_E_RANGE, "row beyond KSK memory");
+    *p = E->d_ksk + (u64)row * kLanes;
+    return ALOHA_OK;
+}
+int aloha_spm_mark_written(aloha_t *E, uint32_t row, uint32_t nrows) {
+    if (!E) return ALOHA_E_ARG;
+    if ((u64)row + nrows > E->cfg.spm_rows) return fail(E, ALOHA_E_RANGE, "rows beyond SPM");
+    int rc = cow_for_host_write(E, (u64)row * kLanes, (u64)nrows * kLanes);
+    if (rc) return rc;
+    mark_written(E, (u64)row * kLanes, (u64)nrows * kLanes);
+    return ALOHA_OK;
+}
+int aloha_set_stream(aloha_t *E, void *stream) {
+    if (!E) return ALOHA_E_ARG;
+    CU(cudaStreamSynchronize(E->stream));
+    E->stream = stream ? (cudaStream_t)stream : E->own_stream;
+    return ALOHA_OK;
+}
+
+int aloha_get_stats(const aloha_t *E, aloha_stats *out) {
+    if (!E || !out) return ALOHA_E_ARG;
+    *out = E->stats;
+    return ALOHA_OK;
+}
+int aloha_get_csr(const aloha_t *E, uint64_t *vl, uint64_t *q, uint64_t *iq) {
+    if (!E) return ALOHA_E_ARG;
+    if (vl) *vl = E->vl;
+    if (q) *q = E->q;
+    if (iq) *iq = E->iq;
+    return ALOHA_OK;
+}
+
+int aloha_decode(const uint8_t word[12], uint64_t csr_step, uint64_t out[17]) {
+    if (!word || !out) return ALOHA_E_ARG;
+    const MicroOp m = expand(parse_word(word), csr_step);
+    const uint64_t f[17] = {m.cfg, m.scalar_cfg, m.b0r, m.b0w, m.b1r, m.b1w, m.alu, m.scalar_alu, m.iconn,
+                            m.scalar_iconn, m.ntt, m.muxo, m.muxi, m.vmu_cfg, m.vmu_scalar_cfg, m.ls, m.scalar_ls};
+    std::memcpy(out, f, sizeof f);
+    return ALOHA_OK;
+}
+
+}  // extern "C"

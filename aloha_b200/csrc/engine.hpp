@@ -1,0 +1,113 @@
+// engine.hpp -- host side of the engine: machine state, instruction-stream batcher, plan cache.
+//
+// Execution model.  aloha_run_vp(_batch) does not interpret instructions one by one on the GPU.
+// The host *symbolically* executes the decoded stream (exactly the reference's architectural
+// semantics: CSR context, bank-port operand routing, VLE/VSE addressing), producing a list of
+// vector ops over device address ranges:
+//   * every vector register is a *location* -- a renaming-pool buffer or an alias of an SPM / KSK
+//     range.  VLE becomes an alias (no copy); VSE of a value produced in the same plan redirects
+//     the producer to write SPM directly (store forwarding); anything that would overwrite an
+//     aliased range first materialises the alias (copy-on-write), so architectural state is exact;
+//   * ops are levelled by their true dependencies (RAW / WAW / WAR on address ranges); ops of one
+//     level and kind -- typically the same instruction position of many RNS limbs, polynomials or
+//     run_vp calls -- become ONE kernel launch with a device-resident job table;
+//   * the resulting plan (launch list + job tables + exit state) is cached by (pc, CSR sets, entry
+//     state), so a steady-state caller pays one hash lookup and a handful of launches.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <deque>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/aloha_b200.h"
+#include "isa.hpp"
+#include "kernels.cuh"
+
+namespace alb {
+
+constexpr u64 kLanes = 128;       // SYS_NUM_LANE  (vp_defines.vh:25) -- layout constant only
+constexpr u64 kIramDepth = 4096;  // IRAM_DEPTH    (vp_defines.vh:31)
+
+enum Space : uint8_t { SP_UNDEF = 0, SP_POOL, SP_SPM, SP_KSK };
+
+struct Loc {
+    Space space = SP_UNDEF;
+    u64 off = 0;   // word offset inside SPM / KSK, or pool buffer index
+    u64 n = 0;     // valid words
+};
+
+enum OpKind : uint8_t { K_EW = 0, K_NTT, K_INTT, K_VAUT, K_VROLI, K_COPY };
+
+struct VecOp {
+    OpKind kind;
+    u32 alu = 0;
+    u32 n = 0;
+    u64 *dst = nullptr;
+    const u64 *a = nullptr, *b = nullptr;
+    u64 s = 0, q = 0, iq = 0, k = 0, kinv = 0;
+    int mod = -1;
+    int level = 0;
+};
+
+struct Launch {
+    OpKind kind;
+    u32 alu, n, njobs;
+    size_t table_off;   // byte offset of the job table inside the plan's device buffer
+};
+
+struct TwTable {
+    Tw *fwd = nullptr, *inv = nullptr;
+    ModulusConsts mc{};
+};
+
+struct Plan {
+    std::vector<Launch> launches;
+    void *d_tables = nullptr;
+    size_t table_bytes = 0;
+    // exit state
+    u64 vl = 0, q = 0, iq = 0;
+    int mod_idx = -1;
+    Loc loc[32];
+    std::vector<std::pair<u64, u64>> written;   // SPM word ranges stored to
+    // accounting
+    u64 instructions = 0, limb_ntts = 0, elided = 0, emitted = 0, kernel_launches = 0;
+    cudaGraphExec_t graph = nullptr;
+};
+
+}  // namespace alb
+
+struct aloha {
+    aloha_cfg cfg{};
+    alb::u64 nmax = 0;
+    unsigned kbits = 0;
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    alb::u64 *d_spm = nullptr, *d_ksk = nullptr, *d_pool = nullptr;
+    alb::u64 spm_words = 0, ksk_words = 0;
+    uint32_t pool_count = 0;
+    std::vector<uint8_t> isram, isram_valid;
+    uint64_t isram_version = 0, tf_version = 0;
+    std::vector<alb::u64> mod_q, mod_psi;
+    std::map<std::pair<int, unsigned>, alb::TwTable> tw_tables;
+    // architectural state (persists across run_vp)
+    alb::u64 vl = 0, q = 0, iq = 0;
+    int mod_idx = -1;
+    alb::Loc loc[32];
+    std::vector<uint8_t> written;   // one flag per 64-byte beat of SPM
+    std::unordered_map<std::string, alb::Plan> plans;
+    aloha_stats stats{};
+    std::string last_error;
+
+    alb::u64 *ptr(const alb::Loc &l) const {
+        switch (l.space) {
+        case alb::SP_POOL: return d_pool + l.off * nmax;
+        case alb::SP_SPM: return d_spm + l.off;
+        case alb::SP_KSK: return d_ksk + l.off;
+        default: return nullptr;
+        }
+    }
+};

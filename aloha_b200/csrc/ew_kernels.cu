@@ -1,0 +1,191 @@
+// ew_kernels.cu -- element-wise RNS ALU, automorphism / rotation and copy kernels for sm_100a.
+//
+// Reference functions replaced:
+//   modalu (src/vp/vxu/modalu.sv:22-46,152-249,351-379)  -> ew_kernel<OP>, mac_kernel
+//   VAUT / VROLI address+sign logic (src/vp/vxu/vxu_lane.sv:594-599) + the Benes-style lane
+//   interconnect (src/vp/iconn/iconn_top.sv:72-138)       -> perm kernels (gather form)
+//   VLE / VSE (src/vp/vmu/*, spm.sv)                      -> copy_kernel (only when the batcher
+//                                                            cannot alias the access away)
+// All of them are HBM-bound streams: 16-byte vector accesses, one job table per launch
+// (blockIdx.y = job), grids sized so every SM holds several CTAs.
+#include "kernels.cuh"
+#include "modarith.cuh"
+
+namespace alb {
+
+extern unsigned long long g_launches;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kVec = 2;                       // u64 per 16-byte access
+constexpr int kPerThread = 4;                 // two 16-byte accesses in flight per operand
+constexpr int kPerBlock = kThreads * kPerThread;
+
+__device__ __forceinline__ ulonglong2 ld2(const u64 *p) {
+    return *reinterpret_cast<const ulonglong2 *>(p);
+}
+__device__ __forceinline__ void st2(u64 *p, u64 a, u64 b) {
+    ulonglong2 v;
+    v.x = a;
+    v.y = b;
+    *reinterpret_cast<ulonglong2 *>(p) = v;
+}
+
+template <u32 OP>
+__global__ void __launch_bounds__(kThreads) ew_kernel(const EwJob *__restrict__ jobs, u32 n) {
+    const EwJob job = jobs[blockIdx.y];
+    constexpr bool kVV = OP == ALU_MUL_VV || OP == ALU_ADD_VV || OP == ALU_SUB_VV;
+    const u64 q = job.q, iq = job.iq, s = job.s;
+#pragma unroll
+    for (int it = 0; it < kPerThread / kVec; ++it) {
+        const u32 i = blockIdx.x * kPerBlock + it * kThreads * kVec + threadIdx.x * kVec;
+        if (i >= n) return;
+        const ulonglong2 a = ld2(job.a + i);
+        ulonglong2 b = a;
+        if (kVV) b = ld2(job.b + i);
+        st2(job.dst + i, rtl_alu<OP>(a.x, b.x, s, q, iq), rtl_alu<OP>(a.y, b.y, s, q, iq));
+    }
+}
+
+// dst = sum_t a[t] * b[t], products and sums exactly as the RTL's VFQMUL.vv / VFQADD.vv chain
+template <int TERMS>
+__global__ void __launch_bounds__(kThreads) mac_kernel(const MacJob *__restrict__ jobs, u32 n) {
+    const MacJob &job = jobs[blockIdx.y];
+    const u64 q = job.q, iq = job.iq;
+#pragma unroll
+    for (int it = 0; it < kPerThread / kVec; ++it) {
+        const u32 i = blockIdx.x * kPerBlock + it * kThreads * kVec + threadIdx.x * kVec;
+        if (i >= n) return;
+        u64 acc0 = 0, acc1 = 0;
+#pragma unroll
+        for (int t = 0; t < TERMS; ++t) {
+            const ulonglong2 a = ld2(job.a[t] + i), b = ld2(job.b[t] + i);
+            const u64 p0 = rtl_alu<ALU_MUL_VV>(a.x, b.x, 0, q, iq);
+            const u64 p1 = rtl_alu<ALU_MUL_VV>(a.y, b.y, 0, q, iq);
+            if (t == 0) { acc0 = p0; acc1 = p1; }
+            else { acc0 = rtl_add(acc0, p0, q); acc1 = rtl_add(acc1, p1, q); }  // both < q already
+        }
+        st2(job.dst + i, acc0, acc1);
+    }
+}
+
+// Gather form of VAUT: destination d takes source i = d * k^-1 mod n; sign from (i*k) mod 2n,
+// which equals d or d + n.  Writes are coalesced 16-byte stores; the strided 8-byte reads hit L2
+// (one limb-polynomial is at most 512 KiB).
+__device__ __forceinline__ u64 aut_gather(const u64 *__restrict__ src, u32 d, u32 n, u64 kinv, u64 k,
+                                          u64 q) {
+    const u32 i = (u32)((u64)d * kinv) & (n - 1);
+    const u64 x = __ldg(src + i);
+    const bool neg = (((u64)i * k) & (2ull * n - 1)) >= n;
+    return neg ? q - x : x;
+}
+
+__global__ void __launch_bounds__(kThreads) vaut_kernel(const PermJob *__restrict__ jobs, u32 n) {
+    const PermJob job = jobs[blockIdx.y];
+    const u64 k = job.k;
+#pragma unroll
+    for (int it = 0; it < kPerThread / kVec; ++it) {
+        const u32 d = blockIdx.x * kPerBlock + it * kThreads * kVec + threadIdx.x * kVec;
+        if (d >= n) return;
+        st2(job.dst + d, aut_gather(job.src, d, n, job.kinv, k, job.q),
+            aut_gather(job.src, d + 1, n, job.kinv, k, job.q));
+    }
+}
+
+// dst[d] = src[(d + rot) mod n]
+__global__ void __launch_bounds__(kThreads) vroli_kernel(const PermJob *__restrict__ jobs, u32 n) {
+    const PermJob job = jobs[blockIdx.y];
+    const u32 rot = (u32)job.kinv;
+#pragma unroll
+    for (int it = 0; it < kPerThread / kVec; ++it) {
+        const u32 d = blockIdx.x * kPerBlock + it * kThreads * kVec + threadIdx.x * kVec;
+        if (d >= n) return;
+        st2(job.dst + d, __ldg(job.src + ((d + rot) & (n - 1))),
+            __ldg(job.src + ((d + 1 + rot) & (n - 1))));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) copy_kernel(const CopyJob *__restrict__ jobs, u32 n) {
+    const CopyJob job = jobs[blockIdx.y];
+#pragma unroll
+    for (int it = 0; it < kPerThread / kVec; ++it) {
+        const u32 i = blockIdx.x * kPerBlock + it * kThreads * kVec + threadIdx.x * kVec;
+        if (i >= n) return;
+        const ulonglong2 v = ld2(job.src + i);
+        st2(job.dst + i, v.x, v.y);
+    }
+}
+
+// dst = c + aut_k(x) * p : VAUT (raw q - x), VFQMUL.vv, VFQADD.vv in one pass.
+__global__ void __launch_bounds__(kThreads) autmac_kernel(const AutMacJob *__restrict__ jobs, u32 n) {
+    const AutMacJob job = jobs[blockIdx.y];
+    const u64 q = job.q, iq = job.iq, k = job.k;
+#pragma unroll
+    for (int it = 0; it < kPerThread / kVec; ++it) {
+        const u32 d = blockIdx.x * kPerBlock + it * kThreads * kVec + threadIdx.x * kVec;
+        if (d >= n) return;
+        const u64 x0 = aut_gather(job.x, d, n, job.kinv, k, q);
+        const u64 x1 = aut_gather(job.x, d + 1, n, job.kinv, k, q);
+        const ulonglong2 p = ld2(job.p + d), c = ld2(job.c + d);
+        const u64 m0 = rtl_alu<ALU_MUL_VV>(x0, p.x, 0, q, iq);
+        const u64 m1 = rtl_alu<ALU_MUL_VV>(x1, p.y, 0, q, iq);
+        st2(job.dst + d, rtl_alu<ALU_ADD_VV>(c.x, m0, 0, q, iq), rtl_alu<ALU_ADD_VV>(c.y, m1, 0, q, iq));
+    }
+}
+
+inline dim3 grid_for(u32 n, u32 njobs) { return dim3((n + kPerBlock - 1) / kPerBlock, njobs); }
+
+}  // namespace
+
+cudaError_t launch_ew(u32 op, const EwJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
+    const dim3 g = grid_for(n, njobs);
+    switch (op) {
+    case ALU_MUL_VV: ew_kernel<ALU_MUL_VV><<<g, kThreads, 0, st>>>(jobs, n); break;
+    case ALU_MUL_VS: ew_kernel<ALU_MUL_VS><<<g, kThreads, 0, st>>>(jobs, n); break;
+    case ALU_ADD_VV: ew_kernel<ALU_ADD_VV><<<g, kThreads, 0, st>>>(jobs, n); break;
+    case ALU_ADD_VS: ew_kernel<ALU_ADD_VS><<<g, kThreads, 0, st>>>(jobs, n); break;
+    case ALU_SUB_VV: ew_kernel<ALU_SUB_VV><<<g, kThreads, 0, st>>>(jobs, n); break;
+    case ALU_SUB_VS: ew_kernel<ALU_SUB_VS><<<g, kThreads, 0, st>>>(jobs, n); break;
+    case ALU_SUB_SV: ew_kernel<ALU_SUB_SV><<<g, kThreads, 0, st>>>(jobs, n); break;
+    case ALU_MOD: ew_kernel<ALU_MOD><<<g, kThreads, 0, st>>>(jobs, n); break;
+    default: return cudaErrorInvalidValue;
+    }
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vaut(const PermJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
+    vaut_kernel<<<grid_for(n, njobs), kThreads, 0, st>>>(jobs, n);
+    ++g_launches;
+    return cudaGetLastError();
+}
+cudaError_t launch_vroli(const PermJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
+    vroli_kernel<<<grid_for(n, njobs), kThreads, 0, st>>>(jobs, n);
+    ++g_launches;
+    return cudaGetLastError();
+}
+cudaError_t launch_copy(const CopyJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
+    copy_kernel<<<grid_for(n, njobs), kThreads, 0, st>>>(jobs, n);
+    ++g_launches;
+    return cudaGetLastError();
+}
+cudaError_t launch_mac(const MacJob *jobs, u32 njobs, u32 terms, u32 n, cudaStream_t st) {
+    const dim3 g = grid_for(n, njobs);
+    switch (terms) {
+    case 1: mac_kernel<1><<<g, kThreads, 0, st>>>(jobs, n); break;
+    case 2: mac_kernel<2><<<g, kThreads, 0, st>>>(jobs, n); break;
+    case 3: mac_kernel<3><<<g, kThreads, 0, st>>>(jobs, n); break;
+    case 4: mac_kernel<4><<<g, kThreads, 0, st>>>(jobs, n); break;
+    default: return cudaErrorInvalidValue;
+    }
+    ++g_launches;
+    return cudaGetLastError();
+}
+cudaError_t launch_autmac(const AutMacJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
+    autmac_kernel<<<grid_for(n, njobs), kThreads, 0, st>>>(jobs, n);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace alb

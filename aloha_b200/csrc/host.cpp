@@ -1,0 +1,165 @@
+// host.cpp -- the host driver: PROGRAM parsing and op-list replay over a modelled DDR.
+//
+// Restates the reference testbench's software-visible flow (sim/top/top_noaxilite_tb.sv):
+//   parse_op :249-298, run_vp :396-417, run_encode :419-448, run_load_cipher :450-472,
+//   run_store_cipher :474-496, copy_spm_to_dram :498-520, run_mul_plain/hom_add/rotate :522-532,
+//   dump_poly :536-565, run :596-638.
+// Everything here sits ABOVE the C-ABI boundary and only calls the aloha_* entry points.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/aloha_b200.h"
+
+namespace {
+
+enum OpType { OP_LOAD = 1, OP_STORE = 2, OP_ENCODE = 3, OP_ENCODE_POST = 4, OP_MUL_PLAIN = 5, OP_HOM_ADD = 6, OP_ROTATE = 7 };
+
+struct HostOp {
+    int type;
+    uint32_t spm_addr, src1, src2, step;
+    uint64_t dram_addr;
+};
+
+constexpr uint32_t kPcEncodePost = 0, kPcMulPlain = 64, kPcHomAdd = 160, kPcKeyswitch = 256;  // tb:63-66
+constexpr uint64_t kDramVpBase = 10485760;                                                     // tb:45
+constexpr uint32_t kLanes = 128;
+
+uint32_t clog2(uint32_t x) { uint32_t l = 0; while ((1u << l) < x) ++l; return l; }
+
+uint64_t pow3_mod(uint32_t e, uint64_t m) {
+    uint64_t r = 1, b = 3 % m;
+    while (e) { if (e & 1) r = r * b % m; b = b * b % m; e >>= 1; }
+    return r;
+}
+
+}  // namespace
+
+struct aloha_host {
+    aloha_t *eng;
+    uint32_t n;
+    std::vector<HostOp> ops;
+    std::vector<uint8_t> dram;
+    std::map<uint32_t, std::vector<uint64_t>> encoder;
+};
+
+extern "C" {
+
+int aloha_host_create(aloha_t *eng, const char *program, uint64_t dram_bytes, uint32_t n, aloha_host_t **out) {
+    if (!eng || !program || !out || !n || (n & (n - 1))) return ALOHA_E_ARG;
+    aloha_host *H = new aloha_host();
+    H->eng = eng;
+    H->n = n;
+    std::istringstream in(program);
+    std::string line;
+    while (std::getline(in, line)) {
+        if (line.find_first_not_of(" \t\r\n") == std::string::npos) continue;
+        unsigned a0, a1, a2;
+        if (std::sscanf(line.c_str(), "%x,%x,%x", &a0, &a1, &a2) != 3) { delete H; return ALOHA_E_ARG; }
+        HostOp op{};
+        op.type = (a0 >> 28) & 0xf;
+        op.spm_addr = a0 & 0x3fff;
+        switch (op.type) {
+        case OP_LOAD: case OP_STORE: case OP_ENCODE: op.dram_addr = ((uint64_t)a1 << 32) | a2; break;
+        case OP_ENCODE_POST: case OP_MUL_PLAIN: case OP_HOM_ADD: op.src1 = a1 & 0x3fff; op.src2 = a2 & 0x3fff; break;
+        case OP_ROTATE: op.step = a1 & 0x3fff; op.src1 = a2 & 0x3fff; break;
+        default: delete H; return ALOHA_E_OPCODE;   // the TB has "TODO: error handle" here
+        }
+        H->ops.push_back(op);
+    }
+    H->dram.assign(dram_bytes, 0);
+    *out = H;
+    return ALOHA_OK;
+}
+
+void aloha_host_destroy(aloha_host_t *H) { delete H; }
+int aloha_host_num_ops(const aloha_host_t *H) { return H ? (int)H->ops.size() : ALOHA_E_ARG; }
+
+int aloha_host_dram_write(aloha_host_t *H, uint64_t addr, const void *src, uint64_t bytes) {
+    if (!H || !src) return ALOHA_E_ARG;
+    if (addr + bytes > H->dram.size()) return ALOHA_E_RANGE;
+    std::memcpy(H->dram.data() + addr, src, bytes);
+    return ALOHA_OK;
+}
+int aloha_host_dram_read(aloha_host_t *H, uint64_t addr, void *dst, uint64_t bytes) {
+    if (!H || !dst) return ALOHA_E_ARG;
+    if (addr + bytes > H->dram.size()) return ALOHA_E_RANGE;
+    std::memcpy(dst, H->dram.data() + addr, bytes);
+    return ALOHA_OK;
+}
+int aloha_host_set_encoder_output(aloha_host_t *H, uint32_t op_index, const uint64_t *data, uint64_t nwords) {
+    if (!H || !data || op_index >= H->ops.size() || nwords != 2ull * H->n) return ALOHA_E_ARG;
+    H->encoder[op_index].assign(data, data + nwords);
+    return ALOHA_OK;
+}
+
+int aloha_host_run_op(aloha_host_t *H, uint32_t i, uint64_t *dump, uint8_t *written, uint64_t *sub_dump,
+                      uint8_t *sub_written, int *has_sub) {
+    if (!H || i >= H->ops.size() || !dump || !written) return ALOHA_E_ARG;
+    const HostOp &op = H->ops[i];
+    const uint64_t words = 4ull * H->n, bytes = words * 8;
+    aloha_t *E = H->eng;
+    int rc = ALOHA_OK;
+    if (has_sub) *has_sub = 0;
+    switch (op.type) {
+    case OP_LOAD: {
+        const uint64_t a = kDramVpBase + op.dram_addr;
+        if (a + bytes > H->dram.size()) return ALOHA_E_RANGE;
+        rc = aloha_dma_mem_h2d(E, op.spm_addr, (const uint64_t *)(H->dram.data() + a), bytes);
+        break;
+    }
+    case OP_STORE: {
+        const uint64_t a = kDramVpBase + op.dram_addr;
+        if (a + bytes > H->dram.size()) return ALOHA_E_RANGE;
+        rc = aloha_dma_mem_d2h(E, (uint64_t *)(H->dram.data() + a), op.spm_addr, bytes);
+        if (rc) return rc;
+        std::memcpy(dump, H->dram.data() + a, bytes);   // the TB dumps straight from DRAM (:608-611)
+        return aloha_spm_written(E, op.spm_addr, words, written);
+    }
+    case OP_ENCODE: {
+        auto it = H->encoder.find(i);
+        if (it == H->encoder.end()) return ALOHA_E_STATE;   // encoder output must be injected
+        rc = aloha_dma_mem_h2d(E, op.spm_addr, it->second.data(), it->second.size() * 8);
+        if (rc) return rc;
+        if (sub_dump && sub_written) {
+            rc = aloha_dma_mem_d2h(E, sub_dump, op.spm_addr, bytes);
+            if (!rc) rc = aloha_spm_written(E, op.spm_addr, words, sub_written);
+            if (rc) return rc;
+            if (has_sub) *has_sub = 1;
+        }
+        rc = aloha_run_vp(E, kPcEncodePost, op.spm_addr, 0, op.spm_addr, 0, 0);
+        break;
+    }
+    case OP_MUL_PLAIN: rc = aloha_run_vp(E, kPcMulPlain, op.src1, op.src2, op.spm_addr, 0, 0); break;
+    case OP_HOM_ADD: rc = aloha_run_vp(E, kPcHomAdd, op.src1, op.src2, op.spm_addr, 0, 0); break;
+    case OP_ROTATE: {
+        // tb:530-532: galois element 3^step mod 2N in the step CSR, key at (clog2(step)-1)*12N/128 rows
+        const uint32_t k = (uint32_t)pow3_mod(op.step, 2ull * H->n);
+        const uint32_t ksk_ptr = (clog2(op.step) - 1) * H->n * 12 / kLanes;
+        rc = aloha_run_vp(E, kPcKeyswitch, op.src1, 0, op.spm_addr, ksk_ptr, k);
+        break;
+    }
+    default: return ALOHA_E_OPCODE;   // encode_post as a host op is parsed but never run by the TB
+    }
+    if (rc) return rc;
+    rc = aloha_dma_mem_d2h(E, dump, op.spm_addr, bytes);
+    if (rc) return rc;
+    return aloha_spm_written(E, op.spm_addr, words, written);
+}
+
+int aloha_write_dump_text(const char *path, const uint64_t *data, const uint8_t *written, uint64_t nwords) {
+    if (!path || !data) return ALOHA_E_ARG;
+    FILE *f = std::fopen(path, "w");
+    if (!f) return ALOHA_E_ARG;
+    for (uint64_t i = 0; i < nwords; ++i) {
+        if (written && !written[i]) std::fputs("x\n", f);
+        else std::fprintf(f, "%llu\n", (unsigned long long)data[i]);
+    }
+    std::fclose(f);
+    return ALOHA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// modarith.cuh -- device-side RNS modular arithmetic for sm_100a (integer IMAD / IADD3 pipes).
+//
+// Two families:
+//  * rtl_*   : word-for-word the reference ALU's arithmetic (one conditional subtract on every
+//              input, the 58/63/61-bit Barrett of src/vp/vxu/modmul.sv:150-252, the 65-bit add of
+//              modalu.sv:228, halfred.sv:23-26).  Used by the element-wise kernels so that ANY
+//              64-bit input word -- canonical or not -- produces the word the RTL would store.
+//  * lazy Shoup/Harvey arithmetic for the NTT kernels.  The reference's NTT stores canonical
+//              residues (< q) for every input below 2q, so any exact algorithm is bit-identical;
+//              these keep values in [0, 16q) (q < 2^60) and reduce once at the end.
+#pragma once
+#include <cstdint>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+namespace alb {
+
+__device__ __forceinline__ u64 prered(u64 x, u64 q) { return x >= q ? x - q : x; }
+
+// x in [0, 2c) -> [0, c)
+__device__ __forceinline__ u64 csub(u64 x, u64 c) { return x >= c ? x - c : x; }
+
+// modmul.sv:150 (prod >> 58), :172 (mid >> 63), :195 (mask 2^61), :216-252.
+__device__ __forceinline__ u64 rtl_barrett(u64 a, u64 b, u64 q, u64 iq) {
+    const u64 plo = a * b, phi = __umul64hi(a, b);
+    const u64 prod_shift = (plo >> 58) | (phi << 6);
+    const u64 mlo = prod_shift * iq, mhi = __umul64hi(prod_shift, iq);
+    const u64 mid_shift = (mlo >> 63) | (mhi << 1);
+    const u64 elo = mid_shift * q;  // only bits [60:0] of estim are used
+    const u64 mask = 1ull << 61;
+    const u64 diff = (((plo & (mask - 1)) | mask) - (elo & (mask - 1))) & (mask - 1);
+    return diff < q ? diff : diff - q;
+}
+
+// modalu.sv:228-229: 65-bit sum compared against q, result truncated to 64 bits.
+__device__ __forceinline__ u64 rtl_add(u64 a, u64 b, u64 q) {
+    const u64 s = a + b;
+    const bool carry = s < a;
+    return (carry || s >= q) ? s - q : s;
+}
+// modalu.sv:249
+__device__ __forceinline__ u64 rtl_sub(u64 a, u64 b, u64 q) { return a >= b ? a - b : q + a - b; }
+// halfred.sv:23-26
+__device__ __forceinline__ u64 rtl_half(u64 x, u64 q) {
+    return (x >> 1) + ((x & 1) ? ((q + 1) >> 1) : 0ull);
+}
+
+// ALU opcodes as the decoder emits them (modalu.sv:22-37)
+enum AluOp : u32 {
+    ALU_MUL_VV = 0x00, ALU_MUL_VS = 0x04, ALU_ADD_VV = 0x01, ALU_ADD_VS = 0x05, ALU_SUB_VV = 0x02,
+    ALU_SUB_VS = 0x06, ALU_SUB_SV = 0x0a, ALU_MOD = 0x03
+};
+
+// One element-wise modalu evaluation (res0 only; CT/GS never reach the element-wise path).
+template <u32 OP>
+__device__ __forceinline__ u64 rtl_alu(u64 a_raw, u64 b_raw, u64 s_red, u64 q, u64 iq) {
+    const u64 a = prered(a_raw, q);
+    if (OP == ALU_MUL_VV) return rtl_barrett(a, prered(b_raw, q), q, iq);
+    if (OP == ALU_MUL_VS) return rtl_barrett(a, s_red, q, iq);
+    if (OP == ALU_MOD) return rtl_barrett(a, 1, q, iq);
+    if (OP == ALU_ADD_VV) return rtl_add(a, prered(b_raw, q), q);
+    if (OP == ALU_ADD_VS) return rtl_add(a, s_red, q);
+    if (OP == ALU_SUB_VV) return rtl_sub(a, prered(b_raw, q), q);
+    if (OP == ALU_SUB_VS) return rtl_sub(a, s_red, q);
+    if (OP == ALU_SUB_SV) return rtl_sub(s_red, a, q);
+    return 0;
+}
+
+// ---- lazy arithmetic for the transforms ---------------------------------------------------
+// Shoup: w' = floor(w * 2^64 / q).  For ANY y < 2^64 the result is y*w mod q in [0, 2q).
+__device__ __forceinline__ u64 mul_shoup(u64 y, u64 w, u64 wp, u64 q) {
+    return y * w - __umul64hi(y, wp) * q;
+}
+
+// x < 2^64, q in (2^59, 2^60), mest = floor(2^91 / q) (32 bits).  floor(x/q) - 1 <= est <= floor(x/q),
+// so x - est*q is in [0, 2q); one conditional subtract makes it canonical.
+__device__ __forceinline__ u64 reduce_full(u64 x, u64 q, u32 mest) {
+    const u32 est = __umulhi((u32)(x >> 32), mest) >> 27;
+    return csub(x - (u64)est * q, q);
+}
+
+}  // namespace alb

@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- limb-NTTs/s at N = 2^16 (BASELINE.json's metric) on N B200s of one node.
+
+Workload (BASELINE.json configs[2]): batched negacyclic NTT, N = 65536, 32 RNS limbs
+(the first 32 primes below 2^60 with q = 1 mod 2^17, psi = minimal primitive 2N-th root), B = 64
+polynomials per limb => 2048 limb-NTTs per step, 1 GiB in + 1 GiB out (larger than the 126 MB L2, so
+no flush is needed between steps).  One step = the instruction stream
+`VSETQ/IQ; VLE; VNTT; VSE` x 32 limbs (aloha_b200.asm.transform_stream) issued for all 64
+polynomials through aloha_run_vp_batch -- the reference-facing C-ABI.
+
+  value : device-resident throughput (inputs already in the engine's SPM in HBM), CUDA-event timed
+  e2e   : the same step with HOST buffers: pinned host -> aloha_dma_mem_h2d -> run -> aloha_dma_mem_d2h
+  roofline : algorithmic bytes (2*N*8 per limb-NTT) / event time of the transform kernels, against the
+             measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline : the oracle (C++ golden model, a port of the RTL's algorithm) on the box's host cores,
+             bounded sample.  `--impl reference` times only that.
+
+Multi-GPU (torchrun, one rank per GPU): the limbs of each polynomial batch are independent units, so
+every rank transforms its own 32-limb x 64-poly shard with no data-path collective ("weak" scaling);
+value = limb-NTTs of all ranks / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N = 65536
+LIMBS = 32
+POLYS = 64
+ROWS_PER_POLY = N // 128
+ALG_BYTES_PER_NTT = 2 * N * 8
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def workload_params():
+    from aloha_b200 import params
+    primes = params.synthetic_primes(LIMBS, 2 * N)
+    psis = [params.min_primitive_root(q, 2 * N) for q in primes]
+    return primes, psis
+
+
+def synth_batch(primes, polys, seed):
+    rng = np.random.default_rng(seed)
+    qv = np.array(primes, dtype=np.uint64)[None, :, None]
+    return rng.integers(0, 1 << 59, (polys, LIMBS, N), dtype=np.uint64) % qv
+
+
+# ------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_ntt_rate(primes, psis, nthreads, seconds_target=12.0):
+    """Oracle NTT on a bounded sample of the same workload; returns (limb-NTTs/s, sample text)."""
+    from oracle import oracle as O
+    tabs = O.NttTables(N, primes, psis)
+    count = max(nthreads * 2, 16)
+    x = synth_batch(primes, 1, 0xA10A)[0]
+    reps = (count + LIMBS - 1) // LIMBS
+    a = np.ascontiguousarray(np.concatenate([x] * reps)[:count])
+    idx = (np.arange(count) % LIMBS).astype(np.uint32)
+    t0 = time.perf_counter()
+    tabs.batch(a, idx, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    done, total = count, dt
+    while total < seconds_target:
+        t0 = time.perf_counter()
+        tabs.batch(a, idx, nthreads=nthreads)
+        total += time.perf_counter() - t0
+        done += count
+    return done / total, f"{done} limb-NTTs (N=2^16, limbs cycled over the 32 primes) in {total:.1f} s"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    primes, psis = workload_params()
+    cores = os.cpu_count() or 1
+    from oracle import oracle as O
+    tabs = O.NttTables(N, primes, psis)
+    count = max(2 * cores, 16)   # one step = a bounded sample: `count` limb-NTTs across all cores
+    x = synth_batch(primes, 1, 0xA10A)[0]
+    a = np.ascontiguousarray(np.concatenate([x] * ((count + LIMBS - 1) // LIMBS))[:count])
+    idx = (np.arange(count) % LIMBS).astype(np.uint32)
+    for _ in range(args.warmup):
+        tabs.batch(a, idx, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tabs.batch(a, idx, nthreads=cores)
+    dt = time.perf_counter() - t0
+    value = args.steps * count / dt
+    sample = f"{count} limb-NTTs per step x {args.steps} steps, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "limb_ntts_per_s_n65536", "value": value, "unit": "limb-NTTs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": value, "unit": "limb-NTTs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "limb-NTTs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config():
+    return {"workload": "batched negacyclic NTT, N=65536, 32 RNS limbs x 64 polynomials per GPU "
+                        "(BASELINE.json configs[2])",
+            "n": N, "limbs": LIMBS, "polys": POLYS, "limb_ntts_per_step_per_gpu": LIMBS * POLYS,
+            "l2": "inputs (1 GiB) + outputs (1 GiB) per step exceed L2; no flush needed",
+            "parallelism": "limb/poly-sharded, no data-path collective"}
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import aloha_b200 as A
+    from aloha_b200 import asm
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    primes, psis = workload_params()
+    per_poly = LIMBS * ROWS_PER_POLY
+    rows = POLYS * per_poly
+    eng = A.Engine(vlmax_bits=N * 64, spm_rows=2 * rows, ksk_rows=0, device=local, moduli=list(zip(primes, psis)))
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.load_isram(asm.transform_stream(N, primes).words(), 0)
+    eng.load_isram(asm.transform_stream(N, primes, inverse=True).words(), 1024)
+    calls = A.Engine.make_args([(b * per_poly, 0, rows + b * per_poly, 0, 0) for b in range(POLYS)])
+    back = A.Engine.make_args([(rows + b * per_poly, 0, b * per_poly, 0, 0) for b in range(POLYS)])
+
+    host_in = torch.empty(POLYS * LIMBS * N, dtype=torch.int64).pin_memory()
+    host_out = torch.empty(POLYS * LIMBS * N, dtype=torch.int64).pin_memory()
+    x = synth_batch(primes, POLYS, 0xA10A + rank)
+    host_in.numpy().view(np.uint64)[:] = x.reshape(-1)
+    nbytes = host_in.numel() * 8
+    eng.dma_mem_h2d(0, (host_in.data_ptr(), nbytes))
+    eng.sync()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    step = lambda: eng.run_vp_batch(0, calls)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    s0 = eng.stats()
+    with ClockSampler(local) as clk:
+        ms = timed(step, args.steps)
+    s1 = eng.stats()
+    launches = s1["kernel_launches"] - s0["kernel_launches"]
+    ntts_per_step = LIMBS * POLYS
+    value = world * ntts_per_step * args.steps / (ms / 1e3)
+
+    # inverse transform rate (same machinery, reported alongside)
+    for _ in range(3):
+        eng.run_vp_batch(1024, back)
+    ms_inv = timed(lambda: eng.run_vp_batch(1024, back), args.steps)
+    inv_value = world * ntts_per_step * args.steps / (ms_inv / 1e3)
+
+    # end to end: host buffers in, host buffers out, every step
+    def e2e_step():
+        eng.dma_mem_h2d(0, (host_in.data_ptr(), nbytes))
+        eng.run_vp_batch(0, calls)
+        eng.dma_mem_d2h(rows, POLYS * LIMBS * N, out=host_out.data_ptr())
+    e2e_step()
+    e2e_steps = max(1, min(args.steps, 5))
+    ms_e2e = timed(e2e_step, e2e_steps)
+    e2e_value = world * ntts_per_step * e2e_steps / (ms_e2e / 1e3)
+
+    ok = True
+    if rank == 0 and world == 1:
+        # cpu_baseline leg, part 1: the oracle checks two limb-polys of what was just timed
+        from oracle import oracle as O
+        got = host_out.numpy().view(np.uint64).reshape(POLYS, LIMBS, N)
+        tabs = O.NttTables(N, primes, psis)
+        sel = np.array([0, LIMBS - 1])
+        ok = bool((got[POLYS - 1, sel] == tabs.batch(x[POLYS - 1, sel].copy(), sel)).all())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        per_gpu_rate = ntts_per_step * args.steps / (ms / 1e3)
+        achieved = per_gpu_rate * ALG_BYTES_PER_NTT / 1e9
+        cores = os.cpu_count() or 1
+        cpu_all, sample_all = cpu_ntt_rate(primes, psis, cores, 10.0) if world == 1 else (None, None)
+        cpu_one, _ = cpu_ntt_rate(primes, psis, 1, 4.0) if world == 1 else (None, None)
+        line = {
+            "metric": "limb_ntts_per_s_n65536", "value": value, "unit": "limb-NTTs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": workload_config(),
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": "limb-NTTs/s", "h2d_bytes_per_step": nbytes,
+                    "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "ntt_fwd_cols<8> + ntt_fwd_rows<8> (one limb-NTT = one column pass + one row pass)",
+                         "algorithmic_bytes_per_limb_ntt": ALG_BYTES_PER_NTT},
+            "intt": {"value": inv_value, "unit": "limb-NTTs/s", "ms_per_step": ms_inv / args.steps},
+            "engine_stats": {k: s1[k] - s0[k] for k in s1},
+        }
+        if world == 1:
+            line["cpu_baseline"] = {"value": cpu_all, "unit": "limb-NTTs/s", "cores": cores, "kind": "port",
+                                    "sample": sample_all, "single_thread": cpu_one, "gpu_output_checked_against_oracle": ok}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    if not ok:
+        sys.exit(3)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

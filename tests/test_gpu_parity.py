@@ -1,0 +1,308 @@
+"""GPU parity tests (run on the B200 box): the CUDA engine, called through the C-ABI, against
+  (1) the committed reference golden fixtures -- every per-op RTL dump of the three tv/ cases and the
+      shipped kernel-level vectors -- bit-exact;
+  (2) the oracle (CPU golden model) on seeded synthetic inputs at sizes it finishes in seconds;
+  (3) size-independent properties at the BASELINE.json sizes (N = 2^16, 32 limbs).
+Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+import golden_util as G
+import aloha_b200 as A
+from aloha_b200 import asm
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FLAG_SETS = [0, A.F_NO_BATCH, A.F_NO_ALIAS, A.F_NO_BATCH | A.F_NO_ALIAS, A.F_GRAPHS]
+
+
+def tv_engine(flags=0):
+    e = A.Engine(flags=flags)
+    for words, pc in G.microcode():
+        e.load_isram(words, pc)
+    return e
+
+
+# ------------------------------------------------------------------ (1) reference golden vectors
+@pytest.mark.parametrize("flags", FLAG_SETS)
+@pytest.mark.parametrize("case,ndumps", [("case0_4_4", 10), ("case1_8_8", 19), ("case2_16_16", 37)])
+def test_tv_replay_bit_exact(case, ndumps, flags):
+    """Replay through the generic driver loop (oracle.replay) with the engine as the machine."""
+    assert G.check_case(tv_engine(flags), case) == ndumps
+
+
+@pytest.mark.parametrize("case", ["case0_4_4", "case1_8_8", "case2_16_16"])
+def test_tv_replay_through_c_host_driver(case):
+    """Same replay, driven by the product's own C++ host driver (aloha_host_*)."""
+    m = G.manifest()
+    n = m["n"]
+    entry = m["cases"][case]
+    eng = tv_engine()
+    ops, dram, enc, ksk = G.case_inputs(case)
+    for row, data in ksk.items():
+        eng.dma_ksk_h2d(row, data)
+    host = A.HostDriver(eng, "\n".join(entry["program"]), n)
+    assert len(host) == len(ops)
+    for i, key in entry["loads"].items():
+        host.dram_write(O.DRAM_VP_BASE + ops[int(i)].dram_addr, G.pool(key))
+    for i, data in enc.items():
+        host.set_encoder_output(i, data)
+    seen = 0
+    for i in range(len(host)):
+        for sub, data, wr in host.run_op(i):
+            name = f"inst_{i}_out" if sub is None else f"inst_{i}_{sub}_out"
+            assert G.poly_hashes(data, wr, n) == entry["dumps"][name], f"{case}/{name}"
+            seen += 1
+    assert seen == len(entry["dumps"])
+    st = eng.stats()
+    assert st["kernel_launches"] > 0 and st["copies_elided"] > 0
+
+
+def test_kernel_level_vectors():
+    eng = tv_engine()
+    for item in G.manifest()["kernels"]:
+        got, want = G.run_kernel_vector(eng, item)
+        assert got == want, (item["case"], item["kernel"])
+
+
+# ------------------------------------------------------------------ (2) oracle, synthetic
+def synth(n, nlimbs):
+    primes = O.synthetic_primes(nlimbs, 1 << 17)          # SURVEY 8(d)3 prime rule
+    psis = [O.min_primitive_root(q, 2 * n) for q in primes]
+    return primes, psis
+
+
+@pytest.mark.parametrize("logn", [8, 9, 10, 11, 12, 13, 14, 15, 16])
+def test_ntt_intt_vs_oracle(logn):
+    n, L = 1 << logn, 3
+    rp = n // 128
+    primes, psis = synth(n, L)
+    eng = A.Engine(vlmax_bits=n * 64, spm_rows=4 * L * rp, ksk_rows=0, moduli=list(zip(primes, psis)))
+    eng.load_isram(asm.transform_stream(n, primes).words(), 0)
+    eng.load_isram(asm.transform_stream(n, primes, inverse=True).words(), 1024)
+    rng = np.random.default_rng(logn)
+    x = np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in primes])
+    # adversarial rows: all q-1 (worst case for the lazy bounds), zeros, and values in [q, 2q)
+    x[0, : n // 4] = primes[0] - 1
+    x[1, : n // 4] = 0
+    x[2, : n // 4] += np.uint64(primes[2])
+    eng.dma_mem_h2d(0, x.reshape(-1))
+    eng.run_vp(0, 0, 0, L * rp)
+    f = eng.dma_mem_d2h(L * rp, L * n).reshape(L, n)
+    tabs = O.NttTables(n, primes, psis)
+    want = tabs.batch(x.copy(), np.arange(L))
+    assert (f == want).all()
+    eng.run_vp(1024, L * rp, 0, 2 * L * rp)
+    back = eng.dma_mem_d2h(2 * L * rp, L * n).reshape(L, n)
+    assert (back == tabs.batch(want.copy(), np.arange(L), inverse=True)).all()
+    assert (back == x % np.array(primes, dtype=np.uint64)[:, None]).all()
+
+
+def test_ntt_all_max_inputs_full_size():
+    """Every coefficient q-1 at N = 2^16: the input that maximises every lazy intermediate."""
+    n, L = 65536, 4
+    rp = n // 128
+    primes, psis = synth(n, L)
+    eng = A.Engine(vlmax_bits=n * 64, spm_rows=2 * L * rp, ksk_rows=0, moduli=list(zip(primes, psis)))
+    eng.load_isram(asm.transform_stream(n, primes).words(), 0)
+    x = np.stack([np.full(n, q - 1, dtype=np.uint64) for q in primes])
+    eng.dma_mem_h2d(0, x.reshape(-1))
+    eng.run_vp(0, 0, 0, L * rp)
+    got = eng.dma_mem_d2h(L * rp, L * n).reshape(L, n)
+    assert (got == O.NttTables(n, primes, psis).batch(x.copy(), np.arange(L))).all()
+
+
+ALU_STREAMS = [("vfqmul", None), ("vfqadd", None), ("vfqsub", None), ("vfqmul", 0x123456789abcdef),
+               ("vfqadd", (1 << 60) + 5), ("vfqsub", 77)]
+ALU_CODE = {("vfqmul", False): 0x00, ("vfqadd", False): 0x01, ("vfqsub", False): 0x02,
+            ("vfqmul", True): 0x04, ("vfqadd", True): 0x05, ("vfqsub", True): 0x06}
+
+
+@pytest.mark.parametrize("op,scalar", ALU_STREAMS)
+def test_elementwise_alu_vs_oracle_raw_words(op, scalar):
+    """Inputs are RAW 64-bit words (not reduced): the engine must store what the RTL ALU would."""
+    n, L = 1024, 2
+    rp = n // 128
+    primes = [O.Q0, O.Q2]
+    eng = A.Engine(vlmax_bits=n * 64, spm_rows=3 * L * rp, ksk_rows=0, moduli=())
+    eng.load_isram(asm.elementwise_stream(n, primes, op, scalar).words(), 0)
+    rng = np.random.default_rng(11)
+    a = rng.integers(0, 2**64, (L, n), dtype=np.uint64)
+    b = rng.integers(0, 2**64, (L, n), dtype=np.uint64)
+    a[:, :256] %= np.uint64(primes[0])
+    b[:, :256] %= np.uint64(primes[0])
+    eng.dma_mem_h2d(0, a.reshape(-1))
+    eng.dma_mem_h2d(L * rp, b.reshape(-1))
+    eng.run_vp(0, 0, L * rp, 2 * L * rp)
+    got = eng.dma_mem_d2h(2 * L * rp, L * n).reshape(L, n)
+    code = ALU_CODE[(op, scalar is not None)]
+    for l, q in enumerate(primes):
+        iq = O.barrett_iq(q)
+        idx = list(range(0, n, 7))
+        want = [O.alu(code, int(a[l, i]), int(b[l, i]), scalar or 0, q, iq)[0] for i in idx]
+        assert [int(got[l, i]) for i in idx] == want
+
+
+def run_single(eng, prog, n, inputs, out_rows):
+    eng.load_isram(prog.words(), 0)
+    for row, data in inputs:
+        eng.dma_mem_h2d(row, data)
+    eng.run_vp(0, 0, 0, out_rows)
+    return eng.dma_mem_d2h(out_rows, n)
+
+
+@pytest.mark.parametrize("n,kbits_n", [(8192, 8192), (4096, 8192), (65536, 65536), (65536, 131072)])
+def test_vaut_vroli_vcpy_vfqmod_vs_oracle(n, kbits_n):
+    """Permutation + base-extension primitives, incl. Galois elements >= N (k is truncated
+    to log2(vlmax/64) bits, so on a vlmax = 64 N machine odd-i signs differ from mathematics)."""
+    rp = n // 128
+    q = O.Q0
+    rng = np.random.default_rng(n)
+    x = rng.integers(0, q, n, dtype=np.uint64)
+    x[:16] = 0                                        # VAUT turns 0 into q (Q2)
+    for step in (1, 2, 8, n // 4):
+        k_csr = pow(3, step, 2 * n)
+        eng = A.Engine(vlmax_bits=kbits_n * 64, spm_rows=4 * rp, ksk_rows=0, moduli=())
+        p = asm.Program().vsetvl(n).vsetq(q).vle(0, 0, 0).vaut(2, 0).vse(2, 2, 0).brk()
+        eng.load_isram(p.words(), 0)
+        eng.dma_mem_h2d(0, x)
+        eng.run_vp(0, 0, 0, rp, 0, k_csr)
+        got = eng.dma_mem_d2h(rp, n)
+        k_seen = k_csr & (kbits_n - 1)
+        assert (got == O.automorph(x, k_seen, q)).all(), (n, step)
+    eng = A.Engine(vlmax_bits=kbits_n * 64, spm_rows=4 * rp, ksk_rows=0, moduli=())
+    for rot in (1, 129, n - 1):
+        p = asm.Program().vsetvl(n).vsetq(q).vle(0, 0, 0).vroli(2, 0, rot).vse(2, 2, 0).brk()
+        got = run_single(eng, p, n, [(0, x)], rp)
+        assert (got == np.roll(x, -rot)).all()
+    raw = rng.integers(0, 2**64, n, dtype=np.uint64)
+    iq = O.barrett_iq(q)
+    for name, code in (("vcpy", 0x05), ("vfqmod", 0x03)):
+        p = asm.Program().vsetvl(n).vsetq(q).vle(0, 0, 0)
+        getattr(p, name)(2, 0)
+        p.vse(2, 2, 0).brk()
+        got = run_single(eng, p, n, [(0, raw)], rp)
+        idx = list(range(0, n, 97))
+        assert [int(got[i]) for i in idx] == [O.alu(code, int(raw[i]), 0, 0, q, iq)[0] for i in idx]
+
+
+def test_rotate_mac_stream_vs_oracle():
+    n, L = 8192, 3
+    rp = n // 128
+    primes, psis = synth(n, L)
+    k = pow(3, 4, 2 * n)
+    eng = A.Engine(vlmax_bits=n * 64, spm_rows=4 * L * rp, ksk_rows=0, moduli=())
+    eng.load_isram(asm.rotate_mac_stream(n, primes).words(), 0)
+    rng = np.random.default_rng(2)
+    x = np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in primes])
+    p = np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in primes])
+    acc = np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in primes])
+    eng.dma_mem_h2d(0, x.reshape(-1))
+    eng.dma_mem_h2d(L * rp, np.concatenate([p.reshape(-1), acc.reshape(-1)]))
+    eng.run_vp(0, 0, L * rp, 3 * L * rp, 0, k)
+    got = eng.dma_mem_d2h(3 * L * rp, L * n).reshape(L, n)
+    want = O.aut_mac_batch(acc.copy(), x, p, k, np.array(primes, dtype=np.uint64), np.arange(L))
+    assert (got == want).all()
+
+
+# ------------------------------------------------------------------ batcher / architectural state
+def test_batch_equals_loop_and_plan_cache():
+    n, L, B = 4096, 2, 5
+    rp = n // 128
+    primes, psis = synth(n, L)
+    prog = asm.transform_stream(n, primes).words()
+    rng = np.random.default_rng(9)
+    x = np.stack([rng.integers(0, primes[l % L], n, dtype=np.uint64) for l in range(B * L)])
+    outs = []
+    for batched in (False, True):
+        eng = A.Engine(vlmax_bits=n * 64, spm_rows=2 * B * L * rp, ksk_rows=0, moduli=list(zip(primes, psis)))
+        eng.load_isram(prog, 0)
+        eng.dma_mem_h2d(0, x.reshape(-1))
+        calls = [(b * L * rp, 0, (B + b) * L * rp, 0, 0) for b in range(B)]
+        for _ in range(3):
+            if batched:
+                eng.run_vp_batch(0, calls)
+            else:
+                for c in calls:
+                    eng.run_vp(0, *c)
+        outs.append(eng.dma_mem_d2h(B * L * rp, B * L * n))
+        st = eng.stats()
+        assert st["plans_reused"] >= 2
+        if batched:   # all B*L transforms of one batch share the two launches of one forward NTT
+            assert st["kernel_launches"] == 3 * 2
+            assert st["copies_emitted"] == 0
+    assert (outs[0] == outs[1]).all()
+
+
+def test_register_alias_survives_memory_overwrite_and_undefined_reads_fail():
+    n = 256
+    q = O.Q0
+    eng = A.Engine(vlmax_bits=n * 64, spm_rows=16, ksk_rows=0, moduli=())
+    load = asm.Program().vsetvl(n).vsetq(q).vle(0, 0, 0).brk()
+    store = asm.Program().vse(0, 2, 0).brk()
+    use_undef = asm.Program().vcpy(2, 5).brk()
+    eng.load_isram(load.words(), 0)
+    eng.load_isram(store.words(), 100)
+    eng.load_isram(use_undef.words(), 200)
+    a = np.arange(n, dtype=np.uint64)
+    eng.dma_mem_h2d(0, a)
+    eng.run_vp(0, 0, 0, 0)                 # v0 aliases SPM rows 0-1
+    eng.dma_mem_h2d(0, a + np.uint64(1000))    # overwrite the aliased rows: v0 must keep the OLD data
+    eng.run_vp(100, 0, 0, 4)
+    assert (eng.dma_mem_d2h(4, n) == a).all()
+    assert (eng.dma_mem_d2h(0, n) == a + np.uint64(1000)).all()
+    with pytest.raises(A.AlohaError) as e:
+        eng.run_vp(200)
+    assert e.value.name == "E_UNDEFINED"
+
+
+def test_illegal_streams_error_codes():
+    n = 256
+    eng = A.Engine(vlmax_bits=n * 64, spm_rows=16, ksk_rows=0, moduli=((O.Q0, pow(O.PSI0, 8192 // n, O.Q0)),))
+    eng.dma_mem_h2d(0, np.zeros(n, dtype=np.uint64))
+    cases = {
+        "E_ILLEGAL": asm.Program().vsetvl(n).vsetq(O.Q0).vle(2, 0, 0).vntt(2, 2).brk(),
+        "E_STATE": asm.Program().vsetvl(n).vsetq(O.Q1).vle(0, 0, 0).vntt(2, 0).brk(),   # no ROM for q1
+        "E_RANGE": asm.Program().vsetvl(n).vle(0, 0, 100).brk(),
+        "E_NOBREAK": asm.Program().vsetvl(n),
+    }
+    for name, prog in cases.items():
+        eng.load_isram(np.zeros((4096, 12), dtype=np.uint8), 0)   # NOPs
+        eng.load_isram(prog.words(), 0)
+        with pytest.raises(A.AlohaError) as e:
+            eng.run_vp(0)
+        assert e.value.name == name, name
+
+
+# ------------------------------------------------------------------ (3) properties at full size
+def test_full_size_roundtrip_and_linearity():
+    """N = 2^16, 32 limbs, 4 polynomials: INTT(NTT(x)) == x, NTT(x + y) == NTT(x) + NTT(y)."""
+    n, L, B = 65536, 32, 4
+    rp = n // 128
+    primes, psis = synth(n, L)
+    rows = B * L * rp
+    eng = A.Engine(vlmax_bits=n * 64, spm_rows=4 * rows, ksk_rows=0, moduli=list(zip(primes, psis)))
+    eng.load_isram(asm.transform_stream(n, primes).words(), 0)
+    eng.load_isram(asm.transform_stream(n, primes, inverse=True).words(), 1024)
+    eng.load_isram(asm.elementwise_stream(n, primes, "vfqadd").words(), 2048)
+    rng = np.random.default_rng(1)
+    qv = np.array(primes, dtype=np.uint64)[None, :, None]
+    x = rng.integers(0, 1 << 59, (B, L, n), dtype=np.uint64) % qv
+    eng.dma_mem_h2d(0, x.reshape(-1))
+    calls = lambda src, dst, src1=0: [(src + b * L * rp, src1 + b * L * rp, dst + b * L * rp, 0, 0) for b in range(B)]
+    eng.run_vp_batch(0, calls(0, rows))                 # F = NTT(x)         at rows
+    eng.run_vp_batch(1024, calls(rows, 2 * rows))       # INTT(F)            at 2*rows
+    back = eng.dma_mem_d2h(2 * rows, B * L * n).reshape(B, L, n)
+    assert (back == x).all()
+    # linearity: polys 0,1 -> NTT(x0 + x1) vs NTT(x0) + NTT(x1)
+    F = eng.dma_mem_d2h(rows, B * L * n).reshape(B, L, n)
+    eng.run_vp(2048, 0, L * rp, 3 * rows)               # x0 + x1 at 3*rows
+    eng.run_vp(0, 3 * rows, 0, 3 * rows + L * rp)       # NTT of that
+    lhs = eng.dma_mem_d2h(3 * rows + L * rp, L * n).reshape(L, n)
+    rhs = (F[0] + F[1]) % qv[0]
+    assert (lhs == rhs).all()
+    # spot-check two limbs of one polynomial against the oracle
+    tabs = O.NttTables(n, primes, psis)
+    sel = np.array([0, 31])
+    assert (F[2, sel] == tabs.batch(x[2, sel].copy(), sel)).all()
