@@ -325,6 +325,7 @@ struct Builder {
             src_reg = m.ntt == 2 ? rd(1) : rd(3);
             if (src_reg == wd) return fail(E, ALOHA_E_ILLEGAL, "VNTT/VINTT with vd == vs1");
             if (mod_idx < 0) return fail(E, ALOHA_E_STATE, "VNTT/VINTT under a modulus with no twiddle ROM (aloha_load_tf_rom)");
+            if (n > 65536) return fail(E, ALOHA_E_STATE, "VNTT/VINTT support N <= 65536");
             o.kind = m.ntt == 2 ? K_NTT : K_INTT;
             o.mod = mod_idx;
             int rc = read_loc(src_reg, n, &o.a);
@@ -443,7 +444,7 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
         return a.n < b.n;
     });
     std::vector<uint8_t> tables;
-    const u64 chunk_bytes = E->cfg.l2_chunk_bytes ? E->cfg.l2_chunk_bytes : (32ull << 20);
+    const u64 chunk_bytes = E->cfg.l2_chunk_bytes ? E->cfg.l2_chunk_bytes : ~0ull;   // default: one launch pair
     size_t i = 0;
     while (i < order.size()) {
         const VecOp &h = ops[order[i]];
@@ -647,7 +648,7 @@ const char *aloha_last_error(const aloha_t *E) { return E ? E->last_error.c_str(
 int aloha_create(const aloha_cfg *cfg, aloha_t **out) {
     if (!cfg || !out) return ALOHA_E_ARG;
     const u64 nmax = cfg->vlmax_bits / 64;
-    if (cfg->vlmax_bits % 64 || nmax < 256 || nmax > 65536 || (nmax & (nmax - 1)) || !cfg->spm_rows) return ALOHA_E_ARG;
+    if (cfg->vlmax_bits % 64 || nmax < 256 || nmax > 131072 || (nmax & (nmax - 1)) || !cfg->spm_rows) return ALOHA_E_ARG;
     aloha *E = new aloha();
     E->cfg = *cfg;
     E->nmax = nmax;

@@ -68,16 +68,45 @@ __device__ __forceinline__ u64 rtl_alu(u64 a_raw, u64 b_raw, u64 s_red, u64 q, u
 }
 
 // ---- lazy arithmetic for the transforms ---------------------------------------------------
-// Shoup: w' = floor(w * 2^64 / q).  For ANY y < 2^64 the result is y*w mod q in [0, 2q).
-__device__ __forceinline__ u64 mul_shoup(u64 y, u64 w, u64 wp, u64 q) {
-    return y * w - __umul64hi(y, wp) * q;
+// The IMAD pipe is the scarce resource on sm_100 (64 thread-ops/clk/SM, half the ALU pipe's rate;
+// tools/intpipe_bench.cu), so every 64-bit accumulation is folded into a multiply-add chain and the
+// conditional subtracts use the cheapest ALU-only form.
+
+// x in [0, 2c), c <= 2^63  ->  [0, c).  x - c wraps negative exactly when x < c: 5 ALU instructions
+// (IADD3, IADD3.X, ISETP on the high word, 2 SEL) instead of the 6 of a 64-bit compare.
+__device__ __forceinline__ u64 csub_s(u64 x, u64 c) {
+    const u64 t = x - c;
+    return ((long long)t < 0) ? x : t;
 }
+
+// acc + y*w - floor(y*wp / 2^64) * q   (mod 2^64), with nq = 2^64 - q.
+// Shoup: wp = floor(w * 2^64 / q); for ANY y < 2^64 the product part is y*w mod q in [0, 2q).
+// 4 IMAD.WIDE (exact mulhi) + 2 IMAD.WIDE + 4 IMAD; the two 64-bit accumulations ride the wides.
+__device__ __forceinline__ u64 shoup_mac(u64 acc, u64 y, u64 w, u64 wp, u64 nq) {
+    const u64 qh = __umul64hi(y, wp);
+    const u32 yl = (u32)y, yh = (u32)(y >> 32), wl = (u32)w, wh = (u32)(w >> 32);
+    const u32 ql = (u32)qh, qhh = (u32)(qh >> 32), nl = (u32)nq, nh = (u32)(nq >> 32);
+    u64 r = acc;
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(r) : "r"(yl), "r"(wl));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(r) : "r"(ql), "r"(nl));
+    u32 hi = (u32)(r >> 32);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(yl), "r"(wh));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(yh), "r"(wl));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(ql), "r"(nh));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(qhh), "r"(nl));
+    return ((u64)hi << 32) | (u32)r;
+}
+__device__ __forceinline__ u64 mul_shoup(u64 y, u64 w, u64 wp, u64 nq) { return shoup_mac(0, y, w, wp, nq); }
 
 // x < 2^64, q in (2^59, 2^60), mest = floor(2^91 / q) (32 bits).  floor(x/q) - 1 <= est <= floor(x/q),
 // so x - est*q is in [0, 2q); one conditional subtract makes it canonical.
-__device__ __forceinline__ u64 reduce_full(u64 x, u64 q, u32 mest) {
+__device__ __forceinline__ u64 reduce_full(u64 x, u64 q, u64 nq, u32 mest) {
     const u32 est = __umulhi((u32)(x >> 32), mest) >> 27;
-    return csub(x - (u64)est * q, q);
+    u64 r = x;
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(r) : "r"(est), "r"((u32)nq));
+    u32 hi = (u32)(r >> 32);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(est), "r"((u32)(nq >> 32)));
+    return csub_s(((u64)hi << 32) | (u32)r, q);
 }
 
 }  // namespace alb

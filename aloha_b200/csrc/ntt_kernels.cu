@@ -16,8 +16,19 @@
 // Each thread keeps 16 coefficients in registers and runs radix-16 (4 stages) between exchanges
 // through shared memory; butterflies are Harvey-lazy with Shoup twiddles on the IMAD pipe, values
 // live in [0, 16q) (q < 2^60) and are reduced to canonical form once, at the very end.
+// Inputs are taken as they are (no pre-reduction): the RTL conditionally subtracts q once, which
+// maps [q, 2q) onto the same residue class, and the final canonical reduction makes the stored word
+// identical for every input below 2q.  Forward bounds: 2q -> (+2q per stage) -> 10q -> csub 8q ->
+// 16q | 8q -> 16q -> 8q -> 16q -> canonical.
 #include "kernels.cuh"
 #include "modarith.cuh"
+
+#ifndef ROWS_MINB
+#define ROWS_MINB 3
+#endif
+#ifndef COLS_MINB
+#define COLS_MINB 3
+#endif
 
 namespace alb {
 
@@ -31,18 +42,19 @@ __device__ __forceinline__ Tw ldtw(const Tw *p) {
     return t;
 }
 
-// CT butterfly, lazy: (x, y) -> (x + w y, x - w y + 2q).  Bound grows by 2q.
-__device__ __forceinline__ void ct_bf(u64 &x, u64 &y, const Tw &t, u64 q, u64 q2) {
-    const u64 m = mul_shoup(y, t.w, t.wp, q);
-    y = x - m + q2;
-    x = x + m;
+// CT butterfly, lazy: (x, y) -> (x + w y, x - w y + 2q).  Bound grows by 2q.  x seeds the
+// multiply-add chain, so x' costs no add; y' = 2x + 2q - x'.
+__device__ __forceinline__ void ct_bf(u64 &x, u64 &y, const Tw &t, u64 nq, u64 q2) {
+    const u64 xp = shoup_mac(x, y, t.w, t.wp, nq);
+    y = (x + x + q2) - xp;
+    x = xp;
 }
 // GS butterfly, Harvey: inputs < 2q, outputs < 2q.
-__device__ __forceinline__ void gs_bf(u64 &x, u64 &y, const Tw &t, u64 q, u64 q2) {
+__device__ __forceinline__ void gs_bf(u64 &x, u64 &y, const Tw &t, u64 nq, u64 q2) {
     const u64 s = x + y;
     const u64 d = x - y + q2;
-    x = csub(s, q2);
-    y = mul_shoup(d, t.w, t.wp, q);
+    x = csub_s(s, q2);
+    y = mul_shoup(d, t.w, t.wp, nq);
 }
 
 }  // namespace
@@ -51,7 +63,7 @@ __device__ __forceinline__ void gs_bf(u64 &x, u64 &y, const Tw &t, u64 q, u64 q2
 // S1 = number of column stages (R = 2^S1 rows).  LA = min(S1,4) stages in phase A on rows
 // r = h + H k (H = R / 2^LA), LB = S1 - LA stages in phase B on rows 16 G + e.
 template <int S1>
-__global__ void __launch_bounds__(256) ntt_fwd_cols(const NttJob *__restrict__ jobs) {
+__global__ void __launch_bounds__(256, COLS_MINB) ntt_fwd_cols(const NttJob *__restrict__ jobs) {
     constexpr int LA = S1 < 4 ? S1 : 4, LB = S1 - LA, E = 1 << LA, R = 1 << S1;
     constexpr int H = R / E;             // threads per column in phase A
     constexpr int W = 256 / H;           // tile width in columns
@@ -61,14 +73,14 @@ __global__ void __launch_bounds__(256) ntt_fwd_cols(const NttJob *__restrict__ j
     const NttJob &job = jobs[blockIdx.x / TILES];
     const int c0 = (blockIdx.x % TILES) * W;
     const int t = threadIdx.x, c = t % W, hg = t / W;
-    const u64 q = job.mc.q, q2 = 2 * q;
+    const u64 q = job.mc.q, q2 = 2 * q, nq = 0 - q;
     const u64 *src = job.src + c0 + c;
     u64 *dst = job.dst + c0 + c;
     const Tw *tw = job.tw;
 
     u64 x[E];
 #pragma unroll
-    for (int k = 0; k < E; ++k) x[k] = prered(src[(size_t)(hg + H * k) * 256], q);
+    for (int k = 0; k < E; ++k) x[k] = src[(size_t)(hg + H * k) * 256];   // < 2q (see header)
 
     // phase A: stage v pairs k-bit (LA-1-v); idx = 2^v + (k >> (LA - v))
 #pragma unroll
@@ -79,18 +91,18 @@ Tw w;
         for (int e = 0; e < E; ++e) {
             if (e & half) continue;
             if ((e & (half - 1)) == 0) w = ldtw(tw + (1 << v) + ((e & ~(2 * half - 1)) >> (LA - v)));
-            ct_bf(x[e], x[e + half], w, q, q2);
+            ct_bf(x[e], x[e + half], w, nq, q2);
         }
     }
     if (LB == 0) {
 #pragma unroll
-        for (int k = 0; k < E; ++k) dst[(size_t)(hg + H * k) * 256] = x[k];  // < q + 2q*LA <= 9q
+        for (int k = 0; k < E; ++k) dst[(size_t)(hg + H * k) * 256] = x[k];  // < 2q + 2q*LA <= 10q
         return;
     }
     // exchange: rows h + H k  ->  rows 16 G + e
     const u64 q8 = 8 * q;
 #pragma unroll
-    for (int k = 0; k < E; ++k) smem[(hg + H * k) * W + c] = csub(x[k], q8);  // 9q -> < 8q
+    for (int k = 0; k < E; ++k) smem[(hg + H * k) * W + c] = csub_s(x[k], q8);  // 10q -> < 8q
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < E; ++e) x[e] = smem[(16 * hg + e) * W + c];
@@ -104,7 +116,7 @@ Tw w;
         for (int e = 0; e < E; ++e) {
             if (e & half) continue;
             if ((e & (half - 1)) == 0) w = ldtw(tw + (1 << s) + ((16 * hg + (e & ~(2 * half - 1))) >> (S1 - s)));
-            ct_bf(x[e], x[e + half], w, q, q2);
+            ct_bf(x[e], x[e + half], w, nq, q2);
         }
     }
 #pragma unroll
@@ -118,7 +130,7 @@ Tw w;
 constexpr int kRowPad = 288;  // 256 + 2 * 16
 
 template <int S1>
-__global__ void __launch_bounds__(256) ntt_fwd_rows(const NttJob *__restrict__ jobs, u32 total_rows) {
+__global__ void __launch_bounds__(256, ROWS_MINB) ntt_fwd_rows(const NttJob *__restrict__ jobs, u32 total_rows) {
     constexpr int R = 1 << S1;
     __shared__ u64 smem[16 * kRowPad];
     const int t = threadIdx.x, hw = t >> 4, h = t & 15;
@@ -126,7 +138,7 @@ __global__ void __launch_bounds__(256) ntt_fwd_rows(const NttJob *__restrict__ j
     if (grow >= total_rows) return;                   // whole half-warp exits together
     const NttJob &job = jobs[grow / R];
     const u32 r = grow % R;
-    const u64 q = job.mc.q, q2 = 2 * q, q8 = 8 * q;
+    const u64 q = job.mc.q, q2 = 2 * q, q8 = 8 * q, nq = 0 - q;
     // the column pass (if any) has already moved the polynomial to job.dst
     const u64 *src = (S1 == 0 ? job.src : job.dst) + (size_t)r * 256;
     u64 *dst = job.dst + (size_t)r * 256;
@@ -137,10 +149,10 @@ __global__ void __launch_bounds__(256) ntt_fwd_rows(const NttJob *__restrict__ j
     u64 x[16];
     if (S1 == 0) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = prered(src[h + 16 * k], q);
+        for (int k = 0; k < 16; ++k) x[k] = src[h + 16 * k];             // < 2q
     } else {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = csub(src[h + 16 * k], q8);  // < 16q -> < 8q
+        for (int k = 0; k < 16; ++k) x[k] = csub_s(src[h + 16 * k], q8);  // < 16q -> < 8q
     }
     // phase A: u = 0..3 pairs k-bit (3-u); idx = 2^u (R + r) + (k >> (4 - u))
 #pragma unroll
@@ -151,12 +163,12 @@ Tw w;
         for (int e = 0; e < 16; ++e) {
             if (e & half) continue;
             if ((e & (half - 1)) == 0) w = ldtw(tw + (rr << u) + ((e & ~(2 * half - 1)) >> (4 - u)));
-            ct_bf(x[e], x[e + half], w, q, q2);
+            ct_bf(x[e], x[e + half], w, nq, q2);
         }
     }
     // exchange h + 16k -> 16g + e   (values < 16q -> < 8q)
 #pragma unroll
-    for (int k = 0; k < 16; ++k) buf[h + 18 * k] = csub(x[k], q8);
+    for (int k = 0; k < 16; ++k) buf[h + 18 * k] = csub_s(x[k], q8);
     __syncwarp();
 #pragma unroll
     for (int e = 0; e < 16; e += 2) {
@@ -173,7 +185,7 @@ Tw w;
         for (int e = 0; e < 16; ++e) {
             if (e & half) continue;
             if ((e & (half - 1)) == 0) w = ldtw(tw + (rr << u) + ((16 * h + (e & ~(2 * half - 1))) >> (8 - u)));
-            ct_bf(x[e], x[e + half], w, q, q2);
+            ct_bf(x[e], x[e + half], w, nq, q2);
         }
     }
     // < 16q -> canonical; store the thread's 128 contiguous bytes
@@ -181,8 +193,8 @@ Tw w;
 #pragma unroll
     for (int e = 0; e < 16; e += 2) {
         ulonglong2 v;
-        v.x = reduce_full(x[e], q, mest);
-        v.y = reduce_full(x[e + 1], q, mest);
+        v.x = reduce_full(x[e], q, nq, mest);
+        v.y = reduce_full(x[e + 1], q, nq, mest);
         *reinterpret_cast<ulonglong2 *>(dst + 16 * h + e) = v;
     }
 }
@@ -190,7 +202,7 @@ Tw w;
 // ============================================================================ inverse: rows
 // GS stages lt = 0..7 (gap 2^lt).  idx = (N >> (lt+1)) + (j >> (lt+1)),  j = r*256 + jj.
 template <int S1>
-__global__ void __launch_bounds__(256) ntt_inv_rows(const NttJob *__restrict__ jobs, u32 total_rows) {
+__global__ void __launch_bounds__(256, ROWS_MINB) ntt_inv_rows(const NttJob *__restrict__ jobs, u32 total_rows) {
     constexpr int R = 1 << S1;
     constexpr int LOGN = S1 + 8;
     __shared__ u64 smem[16 * kRowPad];
@@ -199,7 +211,7 @@ __global__ void __launch_bounds__(256) ntt_inv_rows(const NttJob *__restrict__ j
     if (grow >= total_rows) return;
     const NttJob &job = jobs[grow / R];
     const u32 r = grow % R;
-    const u64 q = job.mc.q, q2 = 2 * q;
+    const u64 q = job.mc.q, q2 = 2 * q, nq = 0 - q;
     const u64 *src = job.src + (size_t)r * 256;
     u64 *dst = job.dst + (size_t)r * 256;
     const Tw *tw = job.tw;
@@ -209,8 +221,8 @@ __global__ void __launch_bounds__(256) ntt_inv_rows(const NttJob *__restrict__ j
 #pragma unroll
     for (int e = 0; e < 16; e += 2) {
         const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + 16 * h + e);
-        x[e] = prered(v.x, q);
-        x[e + 1] = prered(v.y, q);
+        x[e] = v.x;          // < 2q (see header)
+        x[e + 1] = v.y;
     }
     // lt = 0..3 pair e-bit lt
 #pragma unroll
@@ -222,7 +234,7 @@ Tw w;
         for (int e = 0; e < 16; ++e) {
             if (e & half) continue;
             if ((e & (half - 1)) == 0) w = ldtw(tw + base + ((16 * h + (e & ~(2 * half - 1))) >> (lt + 1)));
-            gs_bf(x[e], x[e + half], w, q, q2);
+            gs_bf(x[e], x[e + half], w, nq, q2);
         }
     }
 #pragma unroll
@@ -245,8 +257,8 @@ Tw w;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const u64 s = x[i] + x[i + 8], d = x[i] - x[i + 8] + q2;
-                x[i] = csub(mul_shoup(s, job.mc.ninv, job.mc.ninv_p, q), q);
-                x[i + 8] = csub(mul_shoup(d, job.mc.wninv, job.mc.wninv_p, q), q);
+                x[i] = csub_s(mul_shoup(s, job.mc.ninv, job.mc.ninv_p, nq), q);
+                x[i + 8] = csub_s(mul_shoup(d, job.mc.wninv, job.mc.wninv_p, nq), q);
             }
         } else {
 Tw w;
@@ -254,7 +266,7 @@ Tw w;
             for (int e = 0; e < 16; ++e) {
                 if (e & half) continue;
                 if ((e & (half - 1)) == 0) w = ldtw(tw + base + ((e & ~(2 * half - 1)) >> (lt - 3)));
-                gs_bf(x[e], x[e + half], w, q, q2);
+                gs_bf(x[e], x[e + half], w, nq, q2);
             }
         }
     }
@@ -265,7 +277,7 @@ Tw w;
 // ============================================================================ inverse: columns
 // GS stages lt = 8 .. 8+S1-1, row-distance bit b = lt - 8.  m = 2^(S1-1-b), idx = m + (r >> (b+1)).
 template <int S1>
-__global__ void __launch_bounds__(256) ntt_inv_cols(const NttJob *__restrict__ jobs) {
+__global__ void __launch_bounds__(256, COLS_MINB) ntt_inv_cols(const NttJob *__restrict__ jobs) {
     constexpr int LA = S1 < 4 ? S1 : 4, LB = S1 - LA, E = 1 << LA, R = 1 << S1;
     constexpr int H = R / E, W = 256 / H, TILES = H;
     extern __shared__ u64 smem[];
@@ -273,7 +285,7 @@ __global__ void __launch_bounds__(256) ntt_inv_cols(const NttJob *__restrict__ j
     const NttJob &job = jobs[blockIdx.x / TILES];
     const int c0 = (blockIdx.x % TILES) * W;
     const int t = threadIdx.x, c = t % W, hg = t / W;
-    const u64 q = job.mc.q, q2 = 2 * q;
+    const u64 q = job.mc.q, q2 = 2 * q, nq = 0 - q;
     const u64 *src = job.dst + c0 + c;   // the row pass has already moved the polynomial to job.dst
     u64 *dst = job.dst + c0 + c;
     const Tw *tw = job.tw;
@@ -291,7 +303,7 @@ Tw w;
             for (int e = 0; e < E; ++e) {
                 if (e & half) continue;
                 if ((e & (half - 1)) == 0) w = ldtw(tw + (1 << (S1 - 1 - b)) + ((16 * hg + (e & ~(2 * half - 1))) >> (b + 1)));
-                gs_bf(x[e], x[e + half], w, q, q2);
+                gs_bf(x[e], x[e + half], w, nq, q2);
             }
         }
 #pragma unroll
@@ -311,8 +323,8 @@ Tw w;
 #pragma unroll
             for (int i = 0; i < E / 2; ++i) {
                 const u64 s = x[i] + x[i + E / 2], d = x[i] - x[i + E / 2] + q2;
-                x[i] = csub(mul_shoup(s, job.mc.ninv, job.mc.ninv_p, q), q);
-                x[i + E / 2] = csub(mul_shoup(d, job.mc.wninv, job.mc.wninv_p, q), q);
+                x[i] = csub_s(mul_shoup(s, job.mc.ninv, job.mc.ninv_p, nq), q);
+                x[i + E / 2] = csub_s(mul_shoup(d, job.mc.wninv, job.mc.wninv_p, nq), q);
             }
         } else {
 Tw w;
@@ -320,7 +332,7 @@ Tw w;
             for (int e = 0; e < E; ++e) {
                 if (e & half) continue;
                 if ((e & (half - 1)) == 0) w = ldtw(tw + (1 << (S1 - 1 - b)) + ((e & ~(2 * half - 1)) >> (b + 1 - LB)));
-                gs_bf(x[e], x[e + half], w, q, q2);
+                gs_bf(x[e], x[e + half], w, nq, q2);
             }
         }
     }

@@ -177,8 +177,13 @@ def run_gpu(args):
     primes, psis = workload_params()
     per_poly = LIMBS * ROWS_PER_POLY
     rows = POLYS * per_poly
-    eng = A.Engine(vlmax_bits=N * 64, spm_rows=2 * rows, ksk_rows=0, device=local, moduli=list(zip(primes, psis)))
-    stream = torch.cuda.current_stream()
+    eng = A.Engine(vlmax_bits=N * 64, spm_rows=2 * rows, ksk_rows=0, device=local, moduli=list(zip(primes, psis)),
+                   l2_chunk_bytes=args.chunk_mib << 20)
+    # A dedicated non-default torch stream: the engine launches on it (aloha_set_stream) and the CUDA
+    # events below are recorded on it.  (Stream handle 0 would mean "the engine's own stream".)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
     eng.load_isram(asm.transform_stream(N, primes).words(), 0)
     eng.load_isram(asm.transform_stream(N, primes, inverse=True).words(), 1024)
@@ -221,6 +226,14 @@ def run_gpu(args):
     launches = s1["kernel_launches"] - s0["kernel_launches"]
     ntts_per_step = LIMBS * POLYS
     value = world * ntts_per_step * args.steps / (ms / 1e3)
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": value, "ms_per_step": ms / args.steps, "gpu_launches": launches,
+                              "chunk_mib": args.chunk_mib, "polys": POLYS, "clocks": clk.summary()}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # inverse transform rate (same machinery, reported alongside)
     for _ in range(3):
@@ -286,7 +299,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only (profiling runs)")
+    ap.add_argument("--chunk-mib", type=int, default=0, help="override the engine's L2 chunk size")
+    ap.add_argument("--polys", type=int, default=64)
     args = ap.parse_args()
+    globals()["POLYS"] = args.polys
     if args.impl == "reference":
         run_reference(args)
     else:

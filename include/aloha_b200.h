@@ -70,7 +70,7 @@ typedef struct aloha_cfg {
     int32_t device;           /* CUDA device ordinal */
     uint32_t flags;           /* ALOHA_F_* */
     uint32_t pool_buffers;    /* renaming buffers of vlmax_bits/64 words (0 = 64) */
-    uint64_t l2_chunk_bytes;  /* transform launches are split so one chunk stays L2-resident (0 = 32 MiB) */
+    uint64_t l2_chunk_bytes;  /* split transform launches so one chunk's footprint stays below this (0 = never split) */
 } aloha_cfg;
 
 typedef struct aloha_vp_args {
