@@ -7,12 +7,12 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libaloha_b200.so")
+LIB = os.path.join(HERE, os.environ.get("ALOHA_LIB_NAME", "libaloha_b200.so"))
 SOURCES = ["ntt_kernels.cu", "ew_kernels.cu", "engine.cpp", "host.cpp"]
 HEADERS = ["kernels.cuh", "modarith.cuh", "engine.hpp", "isa.hpp", "../../include/aloha_b200.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
+         "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"] + os.environ.get("ALOHA_NVCC_DEFS", "").split()
 
 
 def stale() -> bool:
@@ -29,7 +29,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.rsplit(".", 1)[0] + ".o")
+        obj = os.path.join(HERE, "build", os.path.basename(LIB) + "." + src.rsplit(".", 1)[0] + ".o")
         cmd = [NVCC, *FLAGS, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

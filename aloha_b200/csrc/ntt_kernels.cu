@@ -20,11 +20,13 @@
 // maps [q, 2q) onto the same residue class, and the final canonical reduction makes the stored word
 // identical for every input below 2q.  Forward bounds: 2q -> (+2q per stage) -> 10q -> csub 8q ->
 // 16q | 8q -> 16q -> 8q -> 16q -> canonical.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "modarith.cuh"
 
 #ifndef ROWS_MINB
-#define ROWS_MINB 3
+#define ROWS_MINB 2
 #endif
 #ifndef COLS_MINB
 #define COLS_MINB 3
@@ -199,6 +201,117 @@ Tw w;
     }
 }
 
+// ---------------------------------------------------------------------------- pipelined rows
+// Persistent variant of ntt_fwd_rows: every half-warp is an independent worker that walks over rows
+// (grid-stride), double-buffering them in shared memory with cp.async so the next row streams in
+// from HBM/L2 while the current one is in the butterflies.  Results leave through the same buffer
+// as fully coalesced 16-byte stores.  No block-level barrier anywhere.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int S1>
+__global__ void __launch_bounds__(256, ROWS_MINB) ntt_fwd_rows_pipe(const NttJob *__restrict__ jobs, u32 total_rows) {
+    constexpr int R = 1 << S1;
+    extern __shared__ __align__(16) u64 smem[];          // [16 half-warps][2 buffers][kRowPad]
+    const int t = threadIdx.x, hw = t >> 4, h = t & 15;
+    u64 *buf0 = smem + hw * 2 * kRowPad;
+    const u32 stride = gridDim.x * 16;
+    u32 grow = blockIdx.x * 16 + hw;
+
+    auto row_src = [&](u32 g) -> const u64 * {
+        const NttJob &job = jobs[g / R];
+        return (S1 == 0 ? job.src : job.dst) + (size_t)(g % R) * 256;
+    };
+    // chunk c (16 bytes = words 2c, 2c+1) of the row lands at padded word 2c + 2*(c >> 3)
+    auto prefetch = [&](u32 g, u64 *buf) {
+        if (g < total_rows) {
+            const u64 *src = row_src(g);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = h + 16 * i;
+                cp_async16(buf + 2 * c + 2 * (c >> 3), src + 2 * c);
+            }
+        }
+        cp_async_commit();
+    };
+
+    prefetch(grow, buf0);
+    for (int it = 0; grow < total_rows; grow += stride, ++it) {
+        u64 *buf = buf0 + (it & 1) * kRowPad;
+        prefetch(grow + stride, buf0 + ((it + 1) & 1) * kRowPad);
+        const NttJob &job = jobs[grow / R];
+        const u32 r = grow % R;
+        const u64 q = job.mc.q, q2 = 2 * q, q8 = 8 * q, nq = 0 - q;
+        const Tw *tw = job.tw;
+        const u32 rr = R + r;
+        cp_async_wait<1>();
+        __syncwarp();
+
+        u64 x[16];
+        if (S1 == 0) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) x[k] = buf[h + 18 * k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) x[k] = csub_s(buf[h + 18 * k], q8);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int half = 8 >> u;
+            Tw w;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                if (e & half) continue;
+                if ((e & (half - 1)) == 0) w = ldtw(tw + (rr << u) + ((e & ~(2 * half - 1)) >> (4 - u)));
+                ct_bf(x[e], x[e + half], w, nq, q2);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) buf[h + 18 * k] = csub_s(x[k], q8);   // same words this lane read
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(buf + 18 * h + e);
+            x[e] = v.x;
+            x[e + 1] = v.y;
+        }
+#pragma unroll
+        for (int u = 4; u < 8; ++u) {
+            const int half = 128 >> u;
+            Tw w;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                if (e & half) continue;
+                if ((e & (half - 1)) == 0) w = ldtw(tw + (rr << u) + ((16 * h + (e & ~(2 * half - 1))) >> (8 - u)));
+                ct_bf(x[e], x[e + half], w, nq, q2);
+            }
+        }
+        const u32 mest = job.mc.mest;
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+            ulonglong2 v;
+            v.x = reduce_full(x[e], q, nq, mest);
+            v.y = reduce_full(x[e + 1], q, nq, mest);
+            *reinterpret_cast<ulonglong2 *>(buf + 18 * h + e) = v;          // same words this lane read
+        }
+        __syncwarp();
+        u64 *dst = job.dst + (size_t)r * 256;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = h + 16 * i;
+            *reinterpret_cast<ulonglong2 *>(dst + 2 * c) =
+                *reinterpret_cast<const ulonglong2 *>(buf + 2 * c + 2 * (c >> 3));
+        }
+        __syncwarp();   // the buffer is refilled by the prefetch issued at the top of the next iteration
+    }
+    cp_async_wait<0>();
+}
+
 // ============================================================================ inverse: rows
 // GS stages lt = 0..7 (gap 2^lt).  idx = (N >> (lt+1)) + (j >> (lt+1)),  j = r*256 + jj.
 template <int S1>
@@ -341,6 +454,13 @@ Tw w;
 }
 
 // ============================================================================ launchers
+// Tunables (read once from the environment: A/B switches for profiling runs).
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+static const int g_rows_pipe = env_int("ALOHA_ROWS_PIPE", 0);
+static const int g_persistent_ctas = env_int("ALOHA_PERSISTENT_CTAS", 148 * 3);
 unsigned long long g_launches = 0;
 unsigned long long kernel_launch_count() { return g_launches; }
 static inline void count_launch() { ++g_launches; }
@@ -355,7 +475,19 @@ static cudaError_t fwd_impl(const NttJob *jobs, u32 njobs, cudaStream_t st) {
         count_launch();
     }
     const u32 rows = njobs * R;
-    ntt_fwd_rows<S1><<<(rows + 15) / 16, 256, 0, st>>>(jobs, rows);
+    if (g_rows_pipe) {
+        static bool attr_set = false;
+        constexpr size_t smem = 16 * 2 * kRowPad * 8;
+        if (!attr_set) {
+            cudaFuncSetAttribute(ntt_fwd_rows_pipe<S1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        const u32 tiles = (rows + 15) / 16;
+        const u32 grid = tiles < (u32)g_persistent_ctas ? tiles : (u32)g_persistent_ctas;
+        ntt_fwd_rows_pipe<S1><<<grid, 256, smem, st>>>(jobs, rows);
+    } else {
+        ntt_fwd_rows<S1><<<(rows + 15) / 16, 256, 0, st>>>(jobs, rows);
+    }
     count_launch();
     return cudaGetLastError();
 }
