@@ -44,7 +44,7 @@ class AlohaError(RuntimeError):
 class _Cfg(C.Structure):
     _fields_ = [("vlmax_bits", C.c_uint64), ("spm_rows", C.c_uint32), ("ksk_rows", C.c_uint32),
                 ("device", C.c_int32), ("flags", C.c_uint32), ("pool_buffers", C.c_uint32),
-                ("l2_chunk_bytes", C.c_uint64)]
+                ("l2_chunk_bytes", C.c_uint64), ("isram_depth", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class VpArgs(C.Structure):
@@ -60,7 +60,7 @@ class _Stats(C.Structure):
 
 EXPORTS = ["aloha_create", "aloha_destroy", "aloha_strerror", "aloha_last_error", "aloha_load_isram",
            "aloha_load_tf_rom", "aloha_dma_mem_h2d", "aloha_dma_mem_d2h", "aloha_dma_ksk_h2d",
-           "aloha_spm_written", "aloha_run_vp", "aloha_run_vp_batch", "aloha_sync",
+           "aloha_spm_written", "aloha_run_vp", "aloha_run_vp_batch", "aloha_run_vp_multi", "aloha_sync",
            "aloha_spm_device_ptr", "aloha_ksk_device_ptr", "aloha_spm_mark_written", "aloha_set_stream",
            "aloha_get_stats", "aloha_get_csr", "aloha_decode", "aloha_host_create",
            "aloha_host_destroy", "aloha_host_num_ops", "aloha_host_dram_write", "aloha_host_dram_read",
@@ -96,6 +96,7 @@ def load_library(rebuild: bool = False) -> C.CDLL:
         "aloha_spm_written": (C.c_int, [vp, u32, u64, p8]),
         "aloha_run_vp": (C.c_int, [vp, u32, u32, u32, u32, u32, u32]),
         "aloha_run_vp_batch": (C.c_int, [vp, u32, u32, C.POINTER(VpArgs)]),
+        "aloha_run_vp_multi": (C.c_int, [vp, u32, C.POINTER(u32), C.POINTER(VpArgs)]),
         "aloha_sync": (C.c_int, [vp]),
         "aloha_spm_device_ptr": (C.c_int, [vp, u32, C.POINTER(vp)]),
         "aloha_ksk_device_ptr": (C.c_int, [vp, u32, C.POINTER(vp)]),
@@ -143,11 +144,11 @@ class Engine:
     """One ALOHA vector processor on one GPU: SPM, KSK memory, 32 vregs and CSRs live in HBM."""
 
     def __init__(self, vlmax_bits=VLMAX_BITS, spm_rows=SPM_ROWS, ksk_rows=KSK_ROWS, device=0, flags=0,
-                 moduli=REFERENCE_MODULI, pool_buffers=0, l2_chunk_bytes=0):
+                 moduli=REFERENCE_MODULI, pool_buffers=0, l2_chunk_bytes=0, isram_depth=0):
         self.L = load_library()
         self.h = C.c_void_p()
         self.nmax = vlmax_bits // 64
-        cfg = _Cfg(vlmax_bits, spm_rows, ksk_rows, device, flags, pool_buffers, l2_chunk_bytes)
+        cfg = _Cfg(vlmax_bits, spm_rows, ksk_rows, device, flags, pool_buffers, l2_chunk_bytes, isram_depth, 0)
         rc = self.L.aloha_create(C.byref(cfg), C.byref(self.h))
         if rc:
             detail = self.L.aloha_last_error(self.h).decode() if self.h else ""
@@ -224,6 +225,13 @@ class Engine:
         if not isinstance(args, C.Array):
             args = self.make_args(args)
         self._ck(self.L.aloha_run_vp_batch(self.h, pc, len(args), args), f"run_vp_batch(pc={pc})")
+
+    def run_vp_multi(self, calls):
+        """calls: iterable of (pc, src0, src1, rslt, ksk_ptr, step) -- one batch, one plan."""
+        calls = list(calls)
+        pcs = (C.c_uint32 * len(calls))(*[c[0] for c in calls])
+        args = self.make_args([c[1:] for c in calls])
+        self._ck(self.L.aloha_run_vp_multi(self.h, len(calls), pcs, args), "run_vp_multi")
 
     def sync(self):
         self._ck(self.L.aloha_sync(self.h), "sync")

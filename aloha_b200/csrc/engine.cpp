@@ -561,10 +561,10 @@ void commit(aloha *E, const Plan &plan) {
     E->stats.copies_emitted += plan.emitted;
 }
 
-std::string plan_key(const aloha *E, uint32_t pc, uint32_t count, const aloha_vp_args *args) {
+std::string plan_key(const aloha *E, const uint32_t *pcs, bool same_pc, uint32_t count, const aloha_vp_args *args) {
     std::string k;
     auto put = [&](const void *p, size_t n) { k.append((const char *)p, n); };
-    put(&pc, 4); put(&count, 4);
+    put(pcs, same_pc ? 4 : 4 * (size_t)count); put(&count, 4);
     put(args, sizeof(aloha_vp_args) * count);
     put(&E->vl, 8); put(&E->q, 8); put(&E->iq, 8); put(&E->mod_idx, 4);
     for (int r = 0; r < 32; ++r) { put(&E->loc[r].space, 1); put(&E->loc[r].off, 8); put(&E->loc[r].n, 8); }
@@ -572,16 +572,17 @@ std::string plan_key(const aloha *E, uint32_t pc, uint32_t count, const aloha_vp
     return k;
 }
 
-int run_batch(aloha *E, uint32_t pc, uint32_t count, const aloha_vp_args *args) {
+// pcs: one entry (same_pc) or `count` entries
+int run_batch(aloha *E, const uint32_t *pcs, bool same_pc, uint32_t count, const aloha_vp_args *args) {
     if (!count) return ALOHA_OK;
-    const std::string key = plan_key(E, pc, count, args);
+    const std::string key = plan_key(E, pcs, same_pc, count, args);
     auto it = E->plans.find(key);
     if (it == E->plans.end()) {
         Builder B(E);
         for (uint32_t c = 0; c < count; ++c) {
             bool brk = false;
-            for (u64 at = pc; !brk; ++at) {
-                if (at >= kIramDepth) return fail(E, ALOHA_E_NOBREAK, "ran off the instruction ROM without BREAK");
+            for (u64 at = same_pc ? pcs[0] : pcs[c]; !brk; ++at) {
+                if (at >= E->iram_depth) return fail(E, ALOHA_E_NOBREAK, "ran off the instruction ROM without BREAK");
                 const Inst in = parse_word(&E->isram[at * 12]);
                 int rc = B.step(in, args[c], &brk);
                 if (rc) return rc;
@@ -680,7 +681,8 @@ int aloha_create(const aloha_cfg *cfg, aloha_t **out) {
         CU(cudaMemsetAsync(E->d_ksk, 0, E->ksk_words * 8, E->stream));
     }
     CU(cudaMalloc(&E->d_pool, (u64)E->pool_count * nmax * 8));
-    E->isram.assign(kIramDepth * 12, 0);
+    E->iram_depth = cfg->isram_depth ? cfg->isram_depth : kIramDepthDefault;
+    E->isram.assign(E->iram_depth * 12, 0);
     E->written.assign((E->spm_words + 7) / 8, 0);
     CU(cudaStreamSynchronize(E->stream));
     return ALOHA_OK;
@@ -700,7 +702,7 @@ void aloha_destroy(aloha_t *E) {
 
 int aloha_load_isram(aloha_t *E, const uint8_t *words, uint32_t n, uint32_t at_pc) {
     if (!E || !words) return ALOHA_E_ARG;
-    if ((u64)at_pc + n > kIramDepth) return fail(E, ALOHA_E_RANGE, "instruction ROM has 4096 entries");
+    if ((u64)at_pc + n > E->iram_depth) return fail(E, ALOHA_E_RANGE, "beyond the instruction ROM (cfg.isram_depth)");
     std::memcpy(&E->isram[(size_t)at_pc * 12], words, (size_t)n * 12);
     ++E->isram_version;
     return ALOHA_OK;
@@ -774,12 +776,17 @@ int aloha_run_vp(aloha_t *E, uint32_t pc, uint32_t src0, uint32_t src1, uint32_t
                  uint32_t step) {
     if (!E) return ALOHA_E_ARG;
     const aloha_vp_args a{src0, src1, rslt, ksk_ptr, step};
-    return run_batch(E, pc, 1, &a);
+    return run_batch(E, &pc, true, 1, &a);
 }
 
 int aloha_run_vp_batch(aloha_t *E, uint32_t pc, uint32_t count, const aloha_vp_args *args) {
     if (!E || (count && !args)) return ALOHA_E_ARG;
-    return run_batch(E, pc, count, args);
+    return run_batch(E, &pc, true, count, args);
+}
+
+int aloha_run_vp_multi(aloha_t *E, uint32_t count, const uint32_t *pcs, const aloha_vp_args *args) {
+    if (!E || (count && (!args || !pcs))) return ALOHA_E_ARG;
+    return run_batch(E, pcs, false, count, args);
 }
 
 int aloha_sync(aloha_t *E) {

@@ -30,7 +30,7 @@
 namespace alb {
 
 constexpr u64 kLanes = 128;       // SYS_NUM_LANE  (vp_defines.vh:25) -- layout constant only
-constexpr u64 kIramDepth = 4096;  // IRAM_DEPTH    (vp_defines.vh:31)
+constexpr u64 kIramDepthDefault = 4096;  // IRAM_DEPTH    (vp_defines.vh:31)
 
 enum Space : uint8_t { SP_UNDEF = 0, SP_POOL, SP_SPM, SP_KSK };
 
@@ -89,6 +89,7 @@ struct aloha {
     alb::u64 *d_spm = nullptr, *d_ksk = nullptr, *d_pool = nullptr;
     alb::u64 spm_words = 0, ksk_words = 0;
     uint32_t pool_count = 0;
+    alb::u64 iram_depth = alb::kIramDepthDefault;
     std::vector<uint8_t> isram, isram_valid;
     uint64_t isram_version = 0, tf_version = 0;
     std::vector<alb::u64> mod_q, mod_psi;

@@ -19,6 +19,7 @@
  *   aloha_run_vp_batch             the same handshake issued back-to-back for `count` CSR sets;
  *                                  architecturally identical to a loop over aloha_run_vp, handed to
  *                                  the batcher in one piece so independent limbs share launches
+ *   aloha_run_vp_multi             ditto, one start pc per call
  *   aloha_host_*                   the testbench's host driver        sim/top/top_noaxilite_tb.sv:249-298 (parse_op),
  *                                                                     :419-532 (run_* tasks), :536-565 (dump_poly), :596-638 (run)
  *
@@ -71,6 +72,8 @@ typedef struct aloha_cfg {
     uint32_t flags;           /* ALOHA_F_* */
     uint32_t pool_buffers;    /* renaming buffers of vlmax_bits/64 words (0 = 64) */
     uint64_t l2_chunk_bytes;  /* split transform launches so one chunk's footprint stays below this (0 = never split) */
+    uint32_t isram_depth;     /* instruction ROM entries, IRAM_DEPTH (vp_defines.vh:31); 0 = 4096 as on the reference */
+    uint32_t reserved;
 } aloha_cfg;
 
 typedef struct aloha_vp_args {
@@ -109,6 +112,9 @@ int aloha_spm_written(aloha_t *, uint32_t spm_row, uint64_t nwords, uint8_t *out
 int aloha_run_vp(aloha_t *, uint32_t pc, uint32_t src0, uint32_t src1, uint32_t rslt,
                  uint32_t ksk_ptr, uint32_t step);
 int aloha_run_vp_batch(aloha_t *, uint32_t pc, uint32_t count, const aloha_vp_args *args);
+/* As aloha_run_vp_batch, with a start pc per call (different microcode kernels in one batch, e.g. the
+ * per-modulus sections of a key-switch stream whose VSETQ immediates differ). */
+int aloha_run_vp_multi(aloha_t *, uint32_t count, const uint32_t *pcs, const aloha_vp_args *args);
 int aloha_sync(aloha_t *);
 
 /* Zero-copy access for callers that already live on the device (and for the multi-GPU host layer,

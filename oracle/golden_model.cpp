@@ -22,7 +22,7 @@ typedef unsigned __int128 u128;
 namespace {
 
 constexpr u64 kLanes = 128;          // vp_defines.vh:25  SYS_NUM_LANE
-constexpr u64 kIramDepth = 4096;     // vp_defines.vh:31
+constexpr u64 kIramDepthDefault = 4096;     // vp_defines.vh:31
 constexpr unsigned kModWidth = 60;   // vxu_lane.sv:539  .mod_width(6'd60)
 
 // ----------------------------------------------------------------------------- arithmetic
@@ -276,7 +276,8 @@ struct gm {
     std::vector<u64> spm, ksk;
     std::vector<uint8_t> spm_written;
     std::vector<std::vector<u64>> vreg;   // 32 registers: bank = reg & 1, index = reg >> 1
-    std::vector<uint8_t> isram;           // kIramDepth x 12
+    u64 iram_depth = kIramDepthDefault;
+    std::vector<uint8_t> isram;           // iram_depth x 12
     std::vector<uint8_t> isram_valid;
     u64 vl = 0, q = 0, iq = 0;            // persist across run_vp
     int tf_item = -1;
@@ -446,8 +447,8 @@ gm_t *gm_create(uint64_t vlmax_bits, uint32_t spm_rows, uint32_t ksk_rows) {
     m->spm_written.assign((size_t)spm_rows * kLanes, 0);
     m->ksk.assign((size_t)ksk_rows * kLanes, 0);
     m->vreg.assign(32, std::vector<u64>(nmax, 0));
-    m->isram.assign(kIramDepth * 12, 0);
-    m->isram_valid.assign(kIramDepth, 0);
+    m->isram.assign(m->iram_depth * 12, 0);
+    m->isram_valid.assign(m->iram_depth, 0);
     return m;
 }
 
@@ -463,7 +464,11 @@ int gm_set_moduli(gm_t *m, const uint64_t *q, const uint64_t *psi, uint32_t n) {
 
 int gm_load_isram(gm_t *m, const uint8_t *words, uint32_t n, uint32_t at_pc) {
     if (!m || !words) return GM_E_ARG;
-    if ((u64)at_pc + n > kIramDepth) return GM_E_RANGE;
+    if ((u64)at_pc + n > m->iram_depth) {   // IRAM_DEPTH is an elaboration parameter: grow on demand
+        m->iram_depth = (u64)at_pc + n;
+        m->isram.resize(m->iram_depth * 12, 0);
+        m->isram_valid.resize(m->iram_depth, 0);
+    }
     std::memcpy(&m->isram[(size_t)at_pc * 12], words, (size_t)n * 12);
     std::memset(&m->isram_valid[at_pc], 1, n);
     return GM_OK;
@@ -502,7 +507,7 @@ int gm_run_vp(gm_t *m, uint32_t pc, uint32_t src0, uint32_t src1, uint32_t rslt,
     if (!m) return GM_E_ARG;
     m->last_count = 0;
     for (u64 at = pc;; ++at) {
-        if (at >= kIramDepth) return GM_E_NOBREAK;
+        if (at >= m->iram_depth) return GM_E_NOBREAK;
         Bundle b = decode(&m->isram[at * 12], step);
         ++m->last_count;
         int rc = exec_bundle(m, b, src0, src1, rslt, ksk_ptr);

@@ -169,6 +169,17 @@ class GoldenModel:
     def run_vp(self, pc, src0=0, src1=0, rslt=0, ksk_ptr=0, step=0):
         _ck(self.L.gm_run_vp(self.h, pc, src0, src1, rslt, ksk_ptr, step), f"run_vp(pc={pc})")
 
+    def run_vp_multi(self, calls):
+        for c in calls:
+            self.run_vp(*c)
+
+    def run_vp_batch(self, pc, calls):
+        for c in calls:
+            self.run_vp(pc, *c)
+
+    def sync(self):
+        pass
+
     def vreg_read(self, reg: int, n: int) -> np.ndarray:
         out = np.empty(n, dtype=np.uint64)
         _ck(self.L.gm_vreg_read(self.h, reg, _p64(out), n), "vreg_read")

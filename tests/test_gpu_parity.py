@@ -333,3 +333,26 @@ def test_bench_workload_single_launch_parity():
     eng.run_vp_batch(1024, [(rows + b * L * rp, 0, b * L * rp, 0, 0) for b in range(B)])
     back = eng.dma_mem_d2h(0, B * L * n).reshape(B, L, n)
     assert (back == x).all()
+
+
+# ------------------------------------------------------------------ limb-sharded key-switch stream
+def _ks_engine_factory(lay, moduli_psi):
+    return A.Engine(vlmax_bits=lay.n * 64, spm_rows=lay.spm_rows, ksk_rows=lay.ksk_rows, moduli=moduli_psi,
+                    pool_buffers=256, isram_depth=16384)
+
+
+def test_generalised_keyswitch_stream_reference_vectors_on_gpu():
+    import test_keyswitch_sharded as T
+    for item in [i for i in G.manifest()["kernels"] if i["op"] == "rotate"]:
+        got, want = T.run_reference_rotate_vector(item, _ks_engine_factory)
+        assert got == want, (item["case"], item["kernel"])
+
+
+@pytest.mark.parametrize("n,L", [(1024, 5), (65536, 3)])
+def test_generalised_keyswitch_stream_vs_oracle(n, L):
+    import test_keyswitch_sharded as T
+    from aloha_b200 import keyswitch as KS
+    gpu = T.run_sharded(n, L, 1, 0, KS.LocalComm(), _ks_engine_factory)
+    cpu = T.run_sharded(n, L, 1, 0, KS.LocalComm())
+    for i in range(L):
+        assert (gpu[i][0] == cpu[i][0]).all() and (gpu[i][1] == cpu[i][1]).all(), i
