@@ -28,7 +28,7 @@ KSK_ROWS = 9216              # src/mem_buf/ksk_mem.sv:12-16
 REFERENCE_MODULI = ((576460825317867521, 3825716582911), (576460924102115329, 79932510954937),
                     (576462951330889729, 101017252977188))
 
-F_NO_BATCH, F_NO_ALIAS, F_GRAPHS = 1, 2, 4
+F_NO_BATCH, F_NO_ALIAS, F_GRAPHS, F_NO_FUSE = 1, 2, 4, 8
 
 _ERRORS = {-1: "E_ARG", -2: "E_RANGE", -3: "E_OPCODE", -4: "E_STATE", -5: "E_ILLEGAL", -6: "E_NOBREAK",
            -7: "E_UNDEFINED", -8: "E_CUDA", -9: "E_NOMEM"}
@@ -55,7 +55,7 @@ class VpArgs(C.Structure):
 class _Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("kernel_launches", "instructions", "plans_built",
                                           "plans_reused", "copies_elided", "copies_emitted",
-                                          "limb_ntts")]
+                                          "limb_ntts", "ops_fused")]
 
 
 EXPORTS = ["aloha_create", "aloha_destroy", "aloha_strerror", "aloha_last_error", "aloha_load_isram",

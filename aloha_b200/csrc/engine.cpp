@@ -3,6 +3,7 @@
 #include "engine.hpp"
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 
@@ -92,10 +93,11 @@ void free_tables(aloha *E) {
     E->tw_tables.clear();
 }
 void free_plans(aloha *E) {
-    for (auto &kv : E->plans) {
-        if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
-        cudaFree(kv.second.d_tables);
-    }
+    for (auto &kv : E->plans)
+        for (auto &pl : kv.second) {
+            if (pl.graph) cudaGraphExecDestroy(pl.graph);
+            cudaFree(pl.d_tables);
+        }
     E->plans.clear();
 }
 
@@ -114,6 +116,16 @@ struct Builder {
     std::vector<int> producer;          // pool buffer -> index of the op that wrote it in this plan
     std::vector<std::pair<u64, u64>> written;
     u64 instructions = 0, limb_ntts = 0, elided = 0, emitted = 0;
+    uint32_t live_in_mask = 0, killed_mask = 0;
+    Loc live_in[32];
+    std::vector<uint8_t> alloc_set;
+
+    // the plan's behaviour depends on where `reg` sat on entry
+    void note_read(int reg) {
+        if (reg < 0 || ((killed_mask | live_in_mask) >> reg) & 1) return;
+        live_in_mask |= 1u << reg;
+        live_in[reg] = E->loc[reg];
+    }
 
     explicit Builder(aloha *e) : E(e), vl(e->vl), q(e->q), iq(e->iq), mod_idx(e->mod_idx) {
         std::vector<uint8_t> used(E->pool_count, 0);
@@ -123,6 +135,7 @@ struct Builder {
         }
         for (u32 b = 0; b < E->pool_count; ++b) if (!used[b]) free_bufs.push_back(b);
         producer.assign(E->pool_count, -1);
+        alloc_set.assign(E->pool_count, 0);
     }
 
     u64 *ptr(const Loc &l) const { return E->ptr(l); }
@@ -134,6 +147,7 @@ struct Builder {
         out->n = n;
         free_bufs.pop_front();
         producer[out->off] = -1;
+        alloc_set[out->off] = 1;
         return ALOHA_OK;
     }
     void release(const Loc &l) {
@@ -143,6 +157,7 @@ struct Builder {
     void define(int vd, const Loc &nl) {
         release(loc[vd]);
         loc[vd] = nl;
+        killed_mask |= 1u << vd;
     }
     void emit_copy(u64 *dst, const u64 *src, u64 n) {
         VecOp o{};
@@ -159,6 +174,7 @@ struct Builder {
         for (int r = 0; r < 32; ++r) {
             if (r == except_reg || loc[r].space != space) continue;
             if (!(loc[r].off < off + n && off < loc[r].off + loc[r].n)) continue;
+            note_read(r);
             Loc nl;
             int rc = alloc(&nl, loc[r].n);
             if (rc) return rc;
@@ -172,6 +188,7 @@ struct Builder {
 
     int read_loc(int reg, u64 n, const u64 **out) {
         if (reg < 0) return fail(E, ALOHA_E_OPCODE, "operand port disabled");
+        note_read(reg);
         const Loc &l = loc[reg];
         if (l.space == SP_UNDEF)
             return fail(E, ALOHA_E_UNDEFINED,
@@ -197,6 +214,7 @@ struct Builder {
 
     int store(int vs, u64 word_off, u64 n) {
         if (vs < 0) return fail(E, ALOHA_E_OPCODE, "VSE source port disabled");
+        note_read(vs);
         if (loc[vs].space == SP_UNDEF) return fail(E, ALOHA_E_UNDEFINED, "VSE of undefined v" + std::to_string(vs));
         if (loc[vs].n < n) return fail(E, ALOHA_E_UNDEFINED, "VSE of a register shorter than vl");
         u64 *M = E->d_spm + word_off;
@@ -379,6 +397,140 @@ struct Builder {
     }
 };
 
+// Peephole fusion over the op list (program order): a VFQMUL.vv whose product feeds exactly one
+// VFQADD.vv and is dead afterwards becomes one multiply-add kernel; if one multiplicand is in turn the
+// single-use, dead output of a VAUT, all three become the gather-multiply-add kernel.  "Dead" = the
+// value is not what any vector register holds when the plan ends (architectural state stays exact).
+// Every fused kernel evaluates the same RTL-exact per-element functions in the same order.
+size_t fuse_ops(std::vector<VecOp> &ops, const Loc *final_loc, const aloha *E) {
+    const size_t n = ops.size();
+    std::vector<int> readers(n, 0), prod_a(n, -1), prod_b(n, -1);
+    std::unordered_map<const u64 *, int> writer;   // pointer -> index of the op whose value it holds now
+    for (size_t i = 0; i < n; ++i) {
+        const VecOp &o = ops[i];
+        auto src = [&](const u64 *p) {
+            auto it = writer.find(p);
+            if (p && it != writer.end()) { ++readers[it->second]; return it->second; }
+            return -1;
+        };
+        prod_a[i] = src(o.a);
+        prod_b[i] = src(o.b);
+        writer[o.dst] = (int)i;
+    }
+    std::vector<uint8_t> live_out(n, 0);
+    for (int r = 0; r < 32; ++r) {
+        auto it = writer.find(E->ptr(final_loc[r]));
+        if (final_loc[r].space != SP_UNDEF && it != writer.end()) live_out[it->second] = 1;
+    }
+    auto single_use_temp = [&](int p) {
+        // the producer's destination must be a renaming-pool buffer: a value stored to SPM is visible
+        const VecOp &o = ops[p];
+        const bool in_pool = o.dst >= E->d_pool && o.dst < E->d_pool + (u64)E->pool_count * E->nmax;
+        return in_pool && readers[p] == 1 && !live_out[p];
+    };
+    size_t fused = 0;
+    for (size_t i = 0; i < n; ++i) {
+        VecOp &add = ops[i];
+        if (add.dead || add.kind != K_EW || add.alu != A_ADDVV) continue;
+        for (int side = 0; side < 2; ++side) {
+            const int pm = side == 0 ? prod_a[i] : prod_b[i];
+            if (pm < 0 || ops[pm].dead || ops[pm].kind != K_EW || ops[pm].alu != A_MULVV) continue;
+            VecOp &mul = ops[pm];
+            if (!single_use_temp(pm) || mul.q != add.q || mul.iq != add.iq || mul.n != add.n) continue;
+            // nothing between the multiply and the add may overwrite the multiply's inputs
+            bool clobbered = false;
+            for (size_t j = pm + 1; j < i && !clobbered; ++j)
+                if (!ops[j].dead && (overlap(ops[j].dst, ops[j].n, mul.a, mul.n) || overlap(ops[j].dst, ops[j].n, mul.b, mul.n)))
+                    clobbered = true;
+            if (clobbered) continue;
+            const u64 *addend = side == 0 ? add.b : add.a;
+            // is one multiplicand a single-use, dead automorphism output?
+            int pa = -1;
+            const u64 *other = nullptr;
+            for (int ms = 0; ms < 2 && pa < 0; ++ms) {
+                const int cand = ms == 0 ? prod_a[pm] : prod_b[pm];
+                if (cand >= 0 && !ops[cand].dead && ops[cand].kind == K_VAUT && ops[cand].q == mul.q && single_use_temp(cand)) {
+                    bool bad = false;
+                    for (size_t j = cand + 1; j < i && !bad; ++j)
+                        if (!ops[j].dead && overlap(ops[j].dst, ops[j].n, ops[cand].a, ops[cand].n)) bad = true;
+                    if (!bad) { pa = cand; other = ms == 0 ? mul.b : mul.a; }
+                }
+            }
+            if (pa >= 0) {
+                add.kind = K_AUTMAC;
+                add.a = ops[pa].a;          // x (gathered)
+                add.b = other;              // p
+                add.k = ops[pa].k;
+                add.kinv = ops[pa].kinv;
+                ops[pa].dead = true;
+                ++fused;
+            } else {
+                add.kind = K_MULADD;
+                add.a = mul.a;
+                add.b = mul.b;
+            }
+            add.c = addend;
+            add.alu = 0;
+            mul.dead = true;
+            ++fused;
+            break;
+        }
+    }
+    // Accumulation chains: acc_t = acc_{t-1} + a_t b_t where acc_{t-1} is itself a single-use, dead
+    // product or multiply-add collapse into one sum-of-products op (same evaluation order).
+    {
+        // recompute producers/readers on the rewritten list (indices unchanged; dead ops skipped)
+        std::fill(readers.begin(), readers.end(), 0);
+        std::vector<int> prod_c(n, -1);
+        writer.clear();
+        for (size_t i = 0; i < n; ++i) {
+            const VecOp &o = ops[i];
+            if (o.dead) continue;
+            auto src = [&](const u64 *p) {
+                auto it = writer.find(p);
+                if (p && it != writer.end()) { ++readers[it->second]; return it->second; }
+                return -1;
+            };
+            src(o.a); src(o.b);
+            prod_c[i] = src(o.c);
+            writer[o.dst] = (int)i;
+        }
+        for (size_t i = 0; i < n; ++i) {
+            VecOp &o = ops[i];
+            if (o.dead || o.kind != K_MULADD) continue;
+            const int pc = prod_c[i];
+            if (pc < 0 || ops[pc].dead || !single_use_temp(pc) || ops[pc].q != o.q || ops[pc].iq != o.iq || ops[pc].n != o.n) continue;
+            VecOp &prev = ops[pc];
+            std::vector<std::pair<const u64 *, const u64 *>> terms;
+            if (prev.kind == K_SOP) terms = prev.terms;
+            else if (prev.kind == K_EW && prev.alu == A_MULVV) terms.emplace_back(prev.a, prev.b);
+            else continue;
+            if (terms.size() >= 1024) continue;
+            // none of the collected operands may be overwritten between the head of the chain and here
+            bool clobbered = false;
+            for (size_t j = pc + 1; j < i && !clobbered; ++j) {
+                if (ops[j].dead) continue;
+                for (auto &tm : terms)
+                    if (overlap(ops[j].dst, ops[j].n, tm.first, o.n) || overlap(ops[j].dst, ops[j].n, tm.second, o.n)) { clobbered = true; break; }
+            }
+            if (clobbered) continue;
+            terms.emplace_back(o.a, o.b);
+            o.kind = K_SOP;
+            o.terms = std::move(terms);
+            o.a = o.b = o.c = nullptr;
+            prev.dead = true;
+            ++fused;
+        }
+    }
+    if (fused) {
+        std::vector<VecOp> kept;
+        kept.reserve(n);
+        for (auto &o : ops) if (!o.dead) kept.push_back(o);
+        ops.swap(kept);
+    }
+    return fused;
+}
+
 // ASAP levels from true dependencies on address ranges.
 struct RangeState { u64 n; int last_write, last_read; };
 
@@ -415,10 +567,14 @@ void assign_levels(std::vector<VecOp> &ops, bool sequential) {
     };
     for (auto &o : ops) {
         int lvl = std::max(scan(o.a, o.n, false), scan(o.b, o.n, false));
+        lvl = std::max(lvl, scan(o.c, o.n, false));
+        for (auto &tm : o.terms) lvl = std::max(lvl, std::max(scan(tm.first, o.n, false), scan(tm.second, o.n, false)));
         lvl = std::max(lvl, scan(o.dst, o.n, true));
         o.level = lvl + 1;
+        for (auto &tm : o.terms) { touch(tm.first, o.n, o.level, false); touch(tm.second, o.n, o.level, false); }
         touch(o.a, o.n, o.level, false);
         touch(o.b, o.n, o.level, false);
+        touch(o.c, o.n, o.level, false);
         touch(o.dst, o.n, o.level, true);
     }
 }
@@ -433,6 +589,7 @@ size_t append(std::vector<uint8_t> &buf, const T &v) {
 
 int compile_plan(aloha *E, Builder &B, Plan *plan) {
     std::vector<VecOp> &ops = B.ops;
+    if (!(E->cfg.flags & (ALOHA_F_NO_BATCH | ALOHA_F_NO_FUSE))) plan->fused = fuse_ops(ops, B.loc, E);
     assign_levels(ops, E->cfg.flags & ALOHA_F_NO_BATCH);
     std::vector<size_t> order(ops.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = i;
@@ -444,6 +601,7 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
         return a.n < b.n;
     });
     std::vector<uint8_t> tables;
+    std::vector<std::pair<size_t, size_t>> fixups;   // (offset of a pointer field, offset it must point to) inside `tables`
     const u64 chunk_bytes = E->cfg.l2_chunk_bytes ? E->cfg.l2_chunk_bytes : ~0ull;   // default: one launch pair
     size_t i = 0;
     while (i < order.size()) {
@@ -460,11 +618,19 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
         for (size_t c = i; c < j;) {
             const size_t cnt = std::min(max_jobs, j - c);
             Launch L{h.kind, h.alu, h.n, (u32)cnt, tables.size()};
+            std::vector<std::pair<size_t, const VecOp *>> sop_jobs;
             for (size_t t = c; t < c + cnt; ++t) {
                 const VecOp &o = ops[order[t]];
                 switch (o.kind) {
                 case K_EW: append(tables, EwJob{o.dst, o.a, o.b, o.s, o.q, o.iq}); break;
                 case K_COPY: append(tables, CopyJob{o.dst, o.a}); break;
+                case K_MULADD: append(tables, MulAddJob{o.dst, o.c, o.a, o.b, o.q, o.iq}); break;
+                case K_SOP: {
+                    const size_t at = append(tables, SopJob{o.dst, nullptr, o.q, o.iq, (u32)o.terms.size(), 0});
+                    sop_jobs.emplace_back(at, &o);
+                    break;
+                }
+                case K_AUTMAC: append(tables, AutMacJob{o.dst, o.c, o.a, o.b, o.q, o.iq, o.k, o.kinv}); break;
                 case K_VAUT:
                 case K_VROLI: append(tables, PermJob{o.dst, o.a, o.q, o.k, o.kinv}); break;
                 case K_NTT:
@@ -478,6 +644,12 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
                 }
                 }
             }
+            for (auto &sj : sop_jobs) {       // operand-pointer lists go right after the launch's job table
+                while (tables.size() % 16) tables.push_back(0);
+                fixups.emplace_back(sj.first + offsetof(SopJob, pairs), tables.size());
+                for (auto &tm : sj.second->terms) { append(tables, tm.first); append(tables, tm.second); }
+            }
+            while (tables.size() % 16) tables.push_back(0);
             plan->launches.push_back(L);
             c += cnt;
         }
@@ -486,12 +658,20 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
     plan->table_bytes = tables.size();
     if (!tables.empty()) {
         CU(cudaMalloc(&plan->d_tables, tables.size()));
+        for (auto &fx : fixups) {
+            const uint8_t *target = (const uint8_t *)plan->d_tables + fx.second;
+            std::memcpy(tables.data() + fx.first, &target, sizeof target);
+        }
         CU(cudaMemcpyAsync(plan->d_tables, tables.data(), tables.size(), cudaMemcpyHostToDevice, E->stream));
         CU(cudaStreamSynchronize(E->stream));   // `tables` is a pageable temporary
     }
     plan->vl = B.vl; plan->q = B.q; plan->iq = B.iq; plan->mod_idx = B.mod_idx;
     for (int r = 0; r < 32; ++r) plan->loc[r] = B.loc[r];
     plan->written = B.written;
+    plan->live_in_mask = B.live_in_mask;
+    plan->killed_mask = B.killed_mask;
+    for (int r = 0; r < 32; ++r) plan->live_in[r] = B.live_in[r];
+    plan->alloc_set = B.alloc_set;
     plan->instructions = B.instructions;
     plan->limb_ntts = B.limb_ntts;
     plan->elided = B.elided;
@@ -508,6 +688,9 @@ int issue(aloha *E, const Plan &plan, u64 *launched) {
         switch (L.kind) {
         case K_EW: e = launch_ew(L.alu, (const EwJob *)tab, L.njobs, L.n, E->stream); break;
         case K_COPY: e = launch_copy((const CopyJob *)tab, L.njobs, L.n, E->stream); break;
+        case K_MULADD: e = launch_muladd((const MulAddJob *)tab, L.njobs, L.n, E->stream); break;
+        case K_SOP: e = launch_sop((const SopJob *)tab, L.njobs, L.n, E->stream); break;
+        case K_AUTMAC: e = launch_autmac((const AutMacJob *)tab, L.njobs, L.n, E->stream); break;
         case K_VAUT: e = launch_vaut((const PermJob *)tab, L.njobs, L.n, E->stream); break;
         case K_VROLI: e = launch_vroli((const PermJob *)tab, L.njobs, L.n, E->stream); break;
         case K_NTT: e = launch_ntt_forward((const NttJob *)tab, L.njobs, ilog2(L.n), E->stream); break;
@@ -553,12 +736,16 @@ void mark_written(aloha *E, u64 word_off, u64 nwords) {
 
 void commit(aloha *E, const Plan &plan) {
     E->vl = plan.vl; E->q = plan.q; E->iq = plan.iq; E->mod_idx = plan.mod_idx;
-    for (int r = 0; r < 32; ++r) E->loc[r] = plan.loc[r];
+    // registers the plan never defined keep their location (an aliased register moved by a
+    // copy-on-write is recorded as read + moved, hence its exit location is the plan's too)
+    for (int r = 0; r < 32; ++r)
+        if (((plan.killed_mask | plan.live_in_mask) >> r) & 1) E->loc[r] = plan.loc[r];
     for (auto &w : plan.written) mark_written(E, w.first, w.second);
     E->stats.instructions += plan.instructions;
     E->stats.limb_ntts += plan.limb_ntts;
     E->stats.copies_elided += plan.elided;
     E->stats.copies_emitted += plan.emitted;
+    E->stats.ops_fused += plan.fused;
 }
 
 std::string plan_key(const aloha *E, const uint32_t *pcs, bool same_pc, uint32_t count, const aloha_vp_args *args) {
@@ -567,17 +754,46 @@ std::string plan_key(const aloha *E, const uint32_t *pcs, bool same_pc, uint32_t
     put(pcs, same_pc ? 4 : 4 * (size_t)count); put(&count, 4);
     put(args, sizeof(aloha_vp_args) * count);
     put(&E->vl, 8); put(&E->q, 8); put(&E->iq, 8); put(&E->mod_idx, 4);
-    for (int r = 0; r < 32; ++r) { put(&E->loc[r].space, 1); put(&E->loc[r].off, 8); put(&E->loc[r].n, 8); }
     put(&E->isram_version, 8); put(&E->tf_version, 8);
     return k;
+}
+
+bool same_loc(const Loc &a, const Loc &b) { return a.space == b.space && a.off == b.off && a.n == b.n; }
+
+// May `plan` be replayed from the machine's current register state?
+bool plan_fits(const aloha *E, const Plan &plan) {
+    for (int r = 0; r < 32; ++r) {
+        const Loc &cur = E->loc[r];
+        if ((plan.live_in_mask >> r) & 1) {
+            if (!same_loc(cur, plan.live_in[r])) return false;
+            continue;
+        }
+        const bool killed = (plan.killed_mask >> r) & 1;
+        if (killed) continue;            // never read, then overwritten: whatever it holds is dead
+        if (cur.space == SP_POOL) {
+            if (plan.alloc_set[cur.off]) return false;   // the plan would scribble on a live value
+        } else if (cur.space == SP_SPM) {
+            // an aliased register whose range the plan stores to would have needed a copy-on-write
+            for (auto &w : plan.written)
+                if (cur.off < w.first + w.second && w.first < cur.off + cur.n) return false;
+        }
+    }
+    return true;
 }
 
 // pcs: one entry (same_pc) or `count` entries
 int run_batch(aloha *E, const uint32_t *pcs, bool same_pc, uint32_t count, const aloha_vp_args *args) {
     if (!count) return ALOHA_OK;
     const std::string key = plan_key(E, pcs, same_pc, count, args);
-    auto it = E->plans.find(key);
-    if (it == E->plans.end()) {
+    if (E->plans.size() >= 1024 && !E->plans.count(key)) {
+        CU(cudaStreamSynchronize(E->stream));
+        free_plans(E);
+    }
+    std::vector<Plan> &cands = E->plans[key];
+    Plan *hit = nullptr;
+    for (auto &pl : cands)
+        if (plan_fits(E, pl)) { hit = &pl; break; }
+    if (!hit) {
         Builder B(E);
         for (uint32_t c = 0; c < count; ++c) {
             bool brk = false;
@@ -591,15 +807,20 @@ int run_batch(aloha *E, const uint32_t *pcs, bool same_pc, uint32_t count, const
         Plan plan;
         int rc = compile_plan(E, B, &plan);
         if (rc) { cudaFree(plan.d_tables); return rc; }
-        if (E->plans.size() >= 512) free_plans(E);
-        it = E->plans.emplace(key, std::move(plan)).first;
+        if (cands.size() >= 16) {            // pathological churn: drop this key's candidates
+            CU(cudaStreamSynchronize(E->stream));
+            for (auto &pl : cands) { if (pl.graph) cudaGraphExecDestroy(pl.graph); cudaFree(pl.d_tables); }
+            cands.clear();
+        }
+        cands.push_back(std::move(plan));
+        hit = &cands.back();
         ++E->stats.plans_built;
     } else {
         ++E->stats.plans_reused;
     }
-    int rc = execute_plan(E, it->second);
+    int rc = execute_plan(E, *hit);
     if (rc) return rc;
-    commit(E, it->second);
+    commit(E, *hit);
     return ALOHA_OK;
 }
 

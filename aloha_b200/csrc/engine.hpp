@@ -40,14 +40,16 @@ struct Loc {
     u64 n = 0;     // valid words
 };
 
-enum OpKind : uint8_t { K_EW = 0, K_NTT, K_INTT, K_VAUT, K_VROLI, K_COPY };
+enum OpKind : uint8_t { K_EW = 0, K_NTT, K_INTT, K_VAUT, K_VROLI, K_COPY, K_MULADD, K_AUTMAC, K_SOP };
 
 struct VecOp {
     OpKind kind;
     u32 alu = 0;
     u32 n = 0;
     u64 *dst = nullptr;
-    const u64 *a = nullptr, *b = nullptr;
+    const u64 *a = nullptr, *b = nullptr, *c = nullptr;   // c: addend of the fused forms
+    bool dead = false;                                     // removed by the fusion pass
+    std::vector<std::pair<const u64 *, const u64 *>> terms;   // K_SOP: dst = sum_t a_t * b_t (in this order)
     u64 s = 0, q = 0, iq = 0, k = 0, kinv = 0;
     int mod = -1;
     int level = 0;
@@ -73,8 +75,15 @@ struct Plan {
     int mod_idx = -1;
     Loc loc[32];
     std::vector<std::pair<u64, u64>> written;   // SPM word ranges stored to
+    // entry conditions under which this plan may be replayed (everything else about the entry
+    // state is irrelevant to it): registers it reads before writing must sit where they sat when it
+    // was built; registers it overwrites may hold anything; the rest must not live in a pool buffer
+    // the plan scribbles on, nor alias an SPM range it stores to.
+    uint32_t live_in_mask = 0, killed_mask = 0;
+    Loc live_in[32];
+    std::vector<uint8_t> alloc_set;             // pool buffers written by the plan
     // accounting
-    u64 instructions = 0, limb_ntts = 0, elided = 0, emitted = 0, kernel_launches = 0;
+    u64 instructions = 0, limb_ntts = 0, elided = 0, emitted = 0, kernel_launches = 0, fused = 0;
     cudaGraphExec_t graph = nullptr;
 };
 
@@ -99,7 +108,7 @@ struct aloha {
     int mod_idx = -1;
     alb::Loc loc[32];
     std::vector<uint8_t> written;   // one flag per 64-byte beat of SPM
-    std::unordered_map<std::string, alb::Plan> plans;
+    std::unordered_map<std::string, std::vector<alb::Plan>> plans;   // key -> candidates (see Plan)
     aloha_stats stats{};
     std::string last_error;
 

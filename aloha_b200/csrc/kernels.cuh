@@ -65,6 +65,22 @@ struct MacJob {
     u64 q, iq;
 };
 
+// dst = c + a * b   (VFQMUL.vv followed by VFQADD.vv, fused)
+struct MulAddJob {
+    u64 *dst;
+    const u64 *c, *a, *b;
+    u64 q, iq;
+};
+
+// dst = ((a_0 b_0 + a_1 b_1) + a_2 b_2) + ...   -- a whole VFQMUL / VFQADD accumulation chain (the
+// key-switch inner product over digits).  pairs[2t], pairs[2t+1] = a_t, b_t.
+struct SopJob {
+    u64 *dst;
+    const u64 *const *pairs;
+    u64 q, iq;
+    u32 terms, pad;
+};
+
 // dst = c + aut_k(x) * p   (rotate-and-sum inner step: VAUT, VFQMUL.vv, VFQADD.vv fused)
 struct AutMacJob {
     u64 *dst;
@@ -82,6 +98,8 @@ cudaError_t launch_vroli(const PermJob *jobs_dev, u32 njobs, u32 n, cudaStream_t
 cudaError_t launch_copy(const CopyJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
 cudaError_t launch_mac(const MacJob *jobs_dev, u32 njobs, u32 terms, u32 n, cudaStream_t st);
 cudaError_t launch_autmac(const AutMacJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
+cudaError_t launch_sop(const SopJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
+cudaError_t launch_muladd(const MulAddJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
 
 // number of kernel launches issued by the launchers above since process start (bench accounting)
 unsigned long long kernel_launch_count();

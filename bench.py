@@ -177,6 +177,26 @@ def run_gpu(args):
     primes, psis = workload_params()
     per_poly = LIMBS * ROWS_PER_POLY
     rows = POLYS * per_poly
+    if args.only:
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+
+        def timed0(fn, steps):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1)
+        if args.only == "keyswitch":
+            out = measure_keyswitch(torch, dist, A, {"device": local}, stream, timed0, world, rank)
+        else:
+            out = measure_rotmac(torch, A, asm, {"device": local}, primes, psis, stream, timed0, 16)
+        if rank == 0:
+            print(json.dumps(out))
+        return
     eng = A.Engine(vlmax_bits=N * 64, spm_rows=2 * rows, ksk_rows=0, device=local, moduli=list(zip(primes, psis)),
                    l2_chunk_bytes=args.chunk_mib << 20)
     # A dedicated non-default torch stream: the engine launches on it (aloha_set_stream) and the CUDA
@@ -241,6 +261,13 @@ def run_gpu(args):
     ms_inv = timed(lambda: eng.run_vp_batch(1024, back), args.steps)
     inv_value = world * ntts_per_step * args.steps / (ms_inv / 1e3)
 
+    extra = {}
+    if not args.no_extra:
+        eng_kwargs = {"device": local}
+        if world == 1:
+            extra["rotate_mac"] = measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, 16)
+        extra["keyswitch"] = measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank)
+
     # end to end: host buffers in, host buffers out, every step
     def e2e_step():
         eng.dma_mem_h2d(0, (host_in.data_ptr(), nbytes))
@@ -283,6 +310,7 @@ def run_gpu(args):
             "intt": {"value": inv_value, "unit": "limb-NTTs/s", "ms_per_step": ms_inv / args.steps},
             "engine_stats": {k: s1[k] - s0[k] for k in s1},
         }
+        line.update(extra)
         if world == 1:
             line["cpu_baseline"] = {"value": cpu_all, "unit": "limb-NTTs/s", "cores": cores, "kind": "port",
                                     "sample": sample_all, "single_thread": cpu_one, "gpu_output_checked_against_oracle": ok}
@@ -291,6 +319,76 @@ def run_gpu(args):
         dist.destroy_process_group()
     if not ok:
         sys.exit(3)
+
+
+def measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, polys):
+    """BASELINE.json configs[3]: per limb acc' = acc + aut_k(x) * p, N = 2^16, 32 limbs x `polys`."""
+    per_poly = LIMBS * ROWS_PER_POLY
+    eng = A.Engine(vlmax_bits=N * 64, spm_rows=4 * polys * per_poly, ksk_rows=0, moduli=(), pool_buffers=128, **eng_kwargs)
+    eng.set_stream(stream.cuda_stream)
+    eng.load_isram(asm.rotate_mac_stream(N, primes).words(), 0)
+    x = synth_batch(primes, polys, 7)
+    eng.dma_mem_h2d(0, x.reshape(-1))                                          # x
+    eng.dma_mem_h2d(polys * per_poly, np.concatenate([x, x], axis=1).reshape(-1))   # [p | acc] per poly
+    k = pow(3, N // 4, 2 * N)                                                  # a Galois element >= N
+    calls = A.Engine.make_args([(b * per_poly, polys * per_poly + 2 * b * per_poly, 3 * polys * per_poly + b * per_poly,
+                                 0, k) for b in range(polys)])
+    for _ in range(3):
+        eng.run_vp_batch(0, calls)
+    s0 = eng.stats()
+    steps = 10
+    ms = timed(lambda: eng.run_vp_batch(0, calls), steps)
+    s1 = eng.stats()
+    per_s = LIMBS * polys * steps / (ms / 1e3)
+    eng.close()
+    return {"value": per_s, "unit": "limb rotate-MACs/s", "ms_per_step": ms / steps, "galois_k": k,
+            "launches_per_step": (s1["kernel_launches"] - s0["kernel_launches"]) / steps,
+            "ops_fused_per_step": (s1["ops_fused"] - s0["ops_fused"]) / steps,
+            "algorithmic_bytes_per_unit": 4 * N * 8,
+            "achieved_gbs_algorithmic": per_s * 4 * N * 8 / 1e9}
+
+
+def measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank, L=47):
+    """BASELINE.json configs[4]: limb-sharded key-switch stream, N = 2^16, L + 1 = 48 limbs."""
+    from aloha_b200 import keyswitch as KS, params
+    pr = params.synthetic_primes(L + 1, 2 * N)
+    P, q = pr[0], pr[1:]
+    psi = [params.min_primitive_root(p, 2 * N) for p in q + [P]]
+    lay = KS.KeySwitchLayout(N, q, P, world, rank)
+    eng = A.Engine(vlmax_bits=N * 64, spm_rows=lay.spm_rows, ksk_rows=lay.ksk_rows,
+                   moduli=list(zip(q + [P], psi)), pool_buffers=6144, isram_depth=32768, **eng_kwargs)
+    eng.set_stream(stream.cuda_stream)
+    comm = KS.TorchComm() if world > 1 else KS.LocalComm()
+    ks = KS.ShardedKeySwitch(eng, lay, comm)
+    rng = np.random.default_rng(100 + rank)
+    for i in lay.owned():
+        m = lay.modulus(i)
+        if i < L:
+            ks.load_input(i, rng.integers(0, m, N, dtype=np.uint64), rng.integers(0, m, N, dtype=np.uint64))
+        ks.load_ksk(i, rng.integers(0, m, 2 * L * N, dtype=np.uint64))
+    k = pow(3, 2, 2 * N)
+    for _ in range(2):
+        ks.run(k)
+    s0 = eng.stats()
+    steps = 5
+    ms = timed(lambda: ks.run(k), steps)
+    s1 = eng.stats()
+    ms_comm = None
+    if world > 1:
+        def only_comm():
+            comm.all_gather_digits(ks)
+            comm.broadcast_t(ks)
+        only_comm()
+        ms_comm = timed(only_comm, steps) / steps
+    eng.close()
+    return {"value": steps / (ms / 1e3), "unit": "key-switches/s", "ms_per_keyswitch": ms / steps,
+            "limbs": L + 1, "limb_ntts_per_keyswitch": KS.transform_count(L),
+            "limb_ntts_per_s": KS.transform_count(L) * steps / (ms / 1e3),
+            "nccl_ms_per_keyswitch": ms_comm, "all_gather_bytes": lay.slots * N * 8,
+            "launches_per_keyswitch_per_rank": (s1["kernel_launches"] - s0["kernel_launches"]) / steps,
+            "plans_built_in_timed_region": s1["plans_built"] - s0["plans_built"],
+            "plans_reused_in_timed_region": s1["plans_reused"] - s0["plans_reused"],
+            "ops_fused_per_keyswitch": (s1["ops_fused"] - s0["ops_fused"]) / steps}
 
 
 def main():
@@ -302,6 +400,8 @@ def main():
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (profiling runs)")
     ap.add_argument("--chunk-mib", type=int, default=0, help="override the engine's L2 chunk size")
     ap.add_argument("--polys", type=int, default=64)
+    ap.add_argument("--no-extra", action="store_true", help="skip the rotate-MAC and key-switch workloads")
+    ap.add_argument("--only", default="", choices=["", "keyswitch", "rotmac"], help="profiling: run one extra workload alone")
     args = ap.parse_args()
     globals()["POLYS"] = args.polys
     if args.impl == "reference":

@@ -61,7 +61,8 @@ enum {
 enum {
     ALOHA_F_NO_BATCH = 1u << 0,  /* one launch per instruction, in program order (debug / parity bisection) */
     ALOHA_F_NO_ALIAS = 1u << 1,  /* materialise every VLE / VSE as a copy (debug) */
-    ALOHA_F_GRAPHS = 1u << 2     /* replay cached plans as CUDA graphs */
+    ALOHA_F_GRAPHS = 1u << 2,    /* replay cached plans as CUDA graphs */
+    ALOHA_F_NO_FUSE = 1u << 3    /* keep VAUT / VFQMUL / VFQADD chains as separate kernels */
 };
 
 typedef struct aloha_cfg {
@@ -87,6 +88,7 @@ typedef struct aloha_stats {
     uint64_t copies_elided;       /* VLE / VSE turned into aliases or forwarded stores */
     uint64_t copies_emitted;      /* VLE / VSE / copy-on-write that needed a copy kernel */
     uint64_t limb_ntts;           /* VNTT + VINTT executed */
+    uint64_t ops_fused;           /* vector ops folded into a fused kernel by the batcher */
 } aloha_stats;
 
 int aloha_create(const aloha_cfg *cfg, aloha_t **out);

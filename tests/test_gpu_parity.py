@@ -14,7 +14,7 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
-FLAG_SETS = [0, A.F_NO_BATCH, A.F_NO_ALIAS, A.F_NO_BATCH | A.F_NO_ALIAS, A.F_GRAPHS]
+FLAG_SETS = [0, A.F_NO_BATCH, A.F_NO_ALIAS, A.F_NO_BATCH | A.F_NO_ALIAS, A.F_GRAPHS, A.F_NO_FUSE]
 
 
 def tv_engine(flags=0):
@@ -204,6 +204,9 @@ def test_rotate_mac_stream_vs_oracle():
     got = eng.dma_mem_d2h(3 * L * rp, L * n).reshape(L, n)
     want = O.aut_mac_batch(acc.copy(), x, p, k, np.array(primes, dtype=np.uint64), np.arange(L))
     assert (got == want).all()
+    # the batcher folds VAUT + VFQMUL + VFQADD of every limb but the last (whose temporaries stay
+    # architecturally visible in v2 / v4) into the gather-multiply-add kernel
+    assert eng.stats()["ops_fused"] == 2 * (L - 1)
 
 
 # ------------------------------------------------------------------ batcher / architectural state
