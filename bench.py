@@ -266,6 +266,7 @@ def run_gpu(args):
         eng_kwargs = {"device": local}
         if world == 1:
             extra["rotate_mac"] = measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, 16)
+            extra["tv_latency"] = measure_tv_latency(A)
         extra["keyswitch"] = measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank)
 
     # end to end: host buffers in, host buffers out, every step
@@ -294,6 +295,11 @@ def run_gpu(args):
         cores = os.cpu_count() or 1
         cpu_all, sample_all = cpu_ntt_rate(primes, psis, cores, 10.0) if world == 1 else (None, None)
         cpu_one, _ = cpu_ntt_rate(primes, psis, 1, 4.0) if world == 1 else (None, None)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ntt_traffic.json")))
+            traffic = tr["total"] * (POLYS * LIMBS / 2048.0)
+        except Exception:
+            traffic = None
         line = {
             "metric": "limb_ntts_per_s_n65536", "value": value, "unit": "limb-NTTs/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -304,7 +310,11 @@ def run_gpu(args):
                     "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "traffic_note": "dram__bytes_read+write of the column + row kernels for one step, from one ncu --set full capture (profiles/r1_ntt_traffic.json)",
+                         "co_bound": {"what": "integer issue (IMAD.WIDE ~2.3 and carry-chain ALU ~1.7 issue cycles per warp instruction; tools/bf_parts.cu)",
+                                      "arithmetic_only_ceiling_limb_ntts_per_s": 1.25e6 * 524288 / 524288,
+                                      "see": "DESIGN.md section 5"},
                          "kernel": "ntt_fwd_cols<8> + ntt_fwd_rows<8> (one limb-NTT = one column pass + one row pass)",
                          "algorithmic_bytes_per_limb_ntt": ALG_BYTES_PER_NTT},
             "intt": {"value": inv_value, "unit": "limb-NTTs/s", "ms_per_step": ms_inv / args.steps},
@@ -319,6 +329,57 @@ def run_gpu(args):
         dist.destroy_process_group()
     if not ok:
         sys.exit(3)
+
+
+def measure_tv_latency(A):
+    """tv-case latency vs CPU (BASELINE.json metric, second half): the three shipped cases replayed
+    end to end (DMA + every run_vp + the per-op dump read-back) on the GPU engine through the C host
+    driver, and on the oracle single-threaded.  Inputs: tests/golden (committed fixtures)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import golden_util as G
+    from oracle import oracle as O
+    out = {}
+    for case in ("case0_4_4", "case1_8_8", "case2_16_16"):
+        m = G.manifest()
+        n, entry = m["n"], m["cases"][case]
+        ops, dram, enc, ksk = G.case_inputs(case)
+
+        def gpu_once():
+            eng = A.Engine()
+            for words, pc in G.microcode():
+                eng.load_isram(words, pc)
+            for row, data in ksk.items():
+                eng.dma_ksk_h2d(row, data)
+            host = A.HostDriver(eng, "\n".join(entry["program"]), n)
+            for i, key in entry["loads"].items():
+                host.dram_write(O.DRAM_VP_BASE + ops[int(i)].dram_addr, G.pool(key))
+            for i, data in enc.items():
+                host.set_encoder_output(i, data)
+            eng.sync()
+            t0 = time.perf_counter()
+            for i in range(len(host)):
+                host.run_op(i)
+            eng.sync()
+            dt = time.perf_counter() - t0
+            t1 = time.perf_counter()          # second pass: plans are cached now (steady state)
+            for i in range(len(host)):
+                host.run_op(i)
+            eng.sync()
+            return dt, time.perf_counter() - t1, eng.stats()
+        first, steady, st = gpu_once()
+        model = O.GoldenModel()
+        for words, pc in G.microcode():
+            model.load_isram(words, pc)
+        for row, data in ksk.items():
+            model.dma_ksk_h2d(row, data)
+        t0 = time.perf_counter()
+        for _ in O.replay(model, ops, dram.copy(), enc, n):
+            pass
+        cpu = time.perf_counter() - t0
+        out[case] = {"ops": len(ops), "gpu_ms_first_run": 1e3 * first, "gpu_ms_steady": 1e3 * steady,
+                     "cpu_oracle_ms_1thread": 1e3 * cpu, "kernel_launches": st["kernel_launches"],
+                     "note": "latency includes every per-op DMA and the 256 KiB dump read-back the testbench does"}
+    return out
 
 
 def measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, polys):
@@ -360,12 +421,19 @@ def measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank, L=
     eng.set_stream(stream.cuda_stream)
     comm = KS.TorchComm() if world > 1 else KS.LocalComm()
     ks = KS.ShardedKeySwitch(eng, lay, comm)
-    rng = np.random.default_rng(100 + rank)
-    for i in lay.owned():
+    def limb_data(i):          # any rank can regenerate any limb's inputs
+        rng = np.random.default_rng(1000 + i)
         m = lay.modulus(i)
-        if i < L:
-            ks.load_input(i, rng.integers(0, m, N, dtype=np.uint64), rng.integers(0, m, N, dtype=np.uint64))
-        ks.load_ksk(i, rng.integers(0, m, 2 * L * N, dtype=np.uint64))
+        return (rng.integers(0, m, N, dtype=np.uint64), rng.integers(0, m, N, dtype=np.uint64),
+                rng.integers(0, m, 2 * L * N, dtype=np.uint64))
+
+    def fill(target, layout):
+        for i in layout.owned():
+            a, b, key = limb_data(i)
+            if i < L:
+                target.load_input(i, a, b)
+            target.load_ksk(i, key)
+    fill(ks, lay)
     k = pow(3, 2, 2 * N)
     for _ in range(2):
         ks.run(k)
@@ -380,11 +448,31 @@ def measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank, L=
             comm.broadcast_t(ks)
         only_comm()
         ms_comm = timed(only_comm, steps) / steps
-    eng.close()
+    sharded_ok = None
+    if world > 1:
+        # every rank re-runs the whole stream alone (no collective) and compares its own output limbs
+        ks.run(k)
+        mine = {i: ks.read_output(i) for i in lay.owned() if i < L}
+        eng.close()
+        lay1 = KS.KeySwitchLayout(N, q, P, 1, 0)
+        eng1 = A.Engine(vlmax_bits=N * 64, spm_rows=lay1.spm_rows, ksk_rows=lay1.ksk_rows,
+                        moduli=list(zip(q + [P], psi)), pool_buffers=6144, isram_depth=32768, **eng_kwargs)
+        eng1.set_stream(stream.cuda_stream)
+        ks1 = KS.ShardedKeySwitch(eng1, lay1, KS.LocalComm())
+        fill(ks1, lay1)
+        ks1.run(k)
+        ok = all((ks1.read_output(i)[0] == v[0]).all() and (ks1.read_output(i)[1] == v[1]).all() for i, v in mine.items())
+        eng1.close()
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        sharded_ok = bool(flag.item())
+    else:
+        eng.close()
     return {"value": steps / (ms / 1e3), "unit": "key-switches/s", "ms_per_keyswitch": ms / steps,
             "limbs": L + 1, "limb_ntts_per_keyswitch": KS.transform_count(L),
             "limb_ntts_per_s": KS.transform_count(L) * steps / (ms / 1e3),
             "nccl_ms_per_keyswitch": ms_comm, "all_gather_bytes": lay.slots * N * 8,
+            "sharded_output_equals_single_gpu": sharded_ok,
             "launches_per_keyswitch_per_rank": (s1["kernel_launches"] - s0["kernel_launches"]) / steps,
             "plans_built_in_timed_region": s1["plans_built"] - s0["plans_built"],
             "plans_reused_in_timed_region": s1["plans_reused"] - s0["plans_reused"],

@@ -1,12 +1,13 @@
-// bf_bench.cu -- arithmetic-only ceiling of the NTT butterfly code shape: 16 coefficients per thread
-// in registers, radix-16 blocks (4 stages x 8 butterflies) repeated, no global/shared traffic in the
-// loop.  Reports butterflies per clock per SM for several occupancies; the NTT kernels cannot exceed
-// this, so (kernel rate / this rate) separates arithmetic cost from memory/exchange cost.
+// bf_bench.cu -- arithmetic-only ceiling of the NTT butterfly code shape: E coefficients per thread
+// in registers, radix-E blocks (log2 E stages) repeated, twiddles read from shared memory per group
+// (as the kernels read them from L1/L2), no global traffic in the loop.  Reports butterflies per
+// clock per SM; the NTT kernels cannot exceed this, so (kernel rate / this rate) separates arithmetic
+// cost from memory / exchange cost.
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "../aloha_b200/csrc/modarith.cuh"
 using namespace alb;
-struct Tw { u64 w, wp; };
+struct __align__(16) Tw { u64 w, wp; };
 
 __device__ __forceinline__ void ct_bf(u64 &x, u64 &y, const Tw &t, u64 nq, u64 q2) {
     const u64 xp = shoup_mac(x, y, t.w, t.wp, nq);
@@ -14,28 +15,51 @@ __device__ __forceinline__ void ct_bf(u64 &x, u64 &y, const Tw &t, u64 nq, u64 q
     x = xp;
 }
 
-template <int MINB>
+template <int LOGE, int MINB>
 __global__ void __launch_bounds__(256, MINB) k(u64 *io, const Tw *tw, u64 q, int iters) {
-    u64 x[16];
+    constexpr int E = 1 << LOGE;
+    __shared__ Tw stw[256];
+    u64 x[E];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int i = 0; i < 16; ++i) x[i] = io[t + i * gridDim.x * blockDim.x];
+    stw[threadIdx.x] = tw[threadIdx.x];
+    __syncthreads();
+    for (int i = 0; i < E; ++i) x[i] = io[t + i * gridDim.x * blockDim.x];
     const u64 q2 = 2 * q, q8 = 8 * q, nq = 0 - q;
-    Tw w[15];
-    for (int i = 0; i < 15; ++i) w[i] = tw[(threadIdx.x & 15) * 16 + i];
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const int half = 8 >> v;
+        for (int v = 0; v < LOGE; ++v) {
+            const int half = E >> (v + 1);
+            Tw w;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
+            for (int e = 0; e < E; ++e) {
                 if (e & half) continue;
-                ct_bf(x[e], x[e + half], w[(1 << v) - 1 + (e >> (4 - v))], nq, q2);
+                if ((e & (half - 1)) == 0) w = stw[((threadIdx.x + it) & 15) * 16 + (1 << v) + (e >> (LOGE - v))];
+                ct_bf(x[e], x[e + half], w, nq, q2);
             }
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = csub_s(x[i], q8);
+        for (int i = 0; i < E; ++i) x[i] = csub_s(x[i], q8);
     }
-    for (int i = 0; i < 16; ++i) io[t + i * gridDim.x * blockDim.x] = x[i];
+    for (int i = 0; i < E; ++i) io[t + i * gridDim.x * blockDim.x] = x[i];
+}
+
+template <int LOGE, int MINB>
+void run(int sms, int clk_khz, u64 *io, Tw *tw, u64 q) {
+    const int iters = 2000, E = 1 << LOGE;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k<LOGE, MINB>);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k<LOGE, MINB>, 256, 0);
+    const int blocks = sms * occ;
+    k<LOGE, MINB><<<blocks, 256>>>(io, tw, q, iters);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0); k<LOGE, MINB><<<blocks, 256>>>(io, tw, q, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double bf = (double)blocks * 256 * (E / 2 * LOGE) * iters;
+    printf("E=%2d minb=%d regs=%3d occ=%d CTA/SM (%2d warps): %.2f bf/clk/SM -> %.2f M limb-NTT/s ceiling\n", E, MINB,
+           fa.numRegs, occ, occ * 8, bf / (ms * 1e-3) / (clk_khz * 1e3) / sms, bf / (ms * 1e-3) / 524288 / 1e6);
 }
 
 int main() {
@@ -43,28 +67,22 @@ int main() {
     cudaGetDeviceProperties(&p, 0);
     int clk_khz;
     cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
-    const int sms = p.multiProcessorCount, iters = 2000;
+    const int sms = p.multiProcessorCount;
     u64 *io; Tw *tw;
     cudaMalloc(&io, (size_t)sms * 8 * 256 * 16 * 8);
     cudaMalloc(&tw, 4096 * sizeof(Tw));
     cudaMemset(io, 1, (size_t)sms * 8 * 256 * 16 * 8);
     cudaMemset(tw, 3, 4096 * sizeof(Tw));
     const u64 q = (1ull << 60) - (1ull << 17) * 7 + 1;
-    for (int ctas = 1; ctas <= 4; ++ctas) {
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
-        auto launch = [&] {
-            if (ctas <= 2) k<2><<<sms * ctas, 256>>>(io, tw, q, iters);
-            else if (ctas == 3) k<3><<<sms * ctas, 256>>>(io, tw, q, iters);
-            else k<4><<<sms * ctas, 256>>>(io, tw, q, iters);
-        };
-        launch(); cudaDeviceSynchronize();
-        cudaEventRecord(e0); launch(); cudaEventRecord(e1); cudaEventSynchronize(e1);
-        float ms; cudaEventElapsedTime(&ms, e0, e1);
-        const double bf = (double)sms * ctas * 256 * 32.0 * iters;
-        printf("%d CTA/SM (%2d warps): %.2f butterflies/clk/SM  (%.2f Gbf/s; one N=2^16 limb-NTT = 524288 bf -> %.2f M limb-NTT/s ceiling)\n",
-               ctas, ctas * 8, bf / (ms * 1e-3) / (clk_khz * 1e3) / sms, bf / ms / 1e6, bf / (ms * 1e-3) / 524288 / 1e6);
-    }
+    run<4, 1>(sms, clk_khz, io, tw, q);
+    run<4, 2>(sms, clk_khz, io, tw, q);
+    run<4, 3>(sms, clk_khz, io, tw, q);
+    run<4, 4>(sms, clk_khz, io, tw, q);
+    run<3, 2>(sms, clk_khz, io, tw, q);
+    run<3, 4>(sms, clk_khz, io, tw, q);
+    run<3, 6>(sms, clk_khz, io, tw, q);
+    run<2, 4>(sms, clk_khz, io, tw, q);
+    run<2, 8>(sms, clk_khz, io, tw, q);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
