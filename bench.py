@@ -313,7 +313,7 @@ def run_gpu(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "traffic_note": "dram__bytes_read+write of the column + row kernels for one step, from one ncu --set full capture (profiles/r1_ntt_traffic.json)",
                          "co_bound": {"what": "integer issue (IMAD.WIDE ~2.3 and carry-chain ALU ~1.7 issue cycles per warp instruction; tools/bf_parts.cu)",
-                                      "arithmetic_only_ceiling_limb_ntts_per_s": 1.25e6 * 524288 / 524288,
+                                      "arithmetic_only_ceiling_limb_ntts_per_s": [1.2e6, 1.55e6], "imad_issue_bound_limb_ntts_per_s": 3.1e6,
                                       "see": "DESIGN.md section 5"},
                          "kernel": "ntt_fwd_cols<8> + ntt_fwd_rows<8> (one limb-NTT = one column pass + one row pass)",
                          "algorithmic_bytes_per_limb_ntt": ALG_BYTES_PER_NTT},
