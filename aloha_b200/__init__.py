@@ -60,6 +60,7 @@ class _Stats(C.Structure):
 
 EXPORTS = ["aloha_create", "aloha_destroy", "aloha_strerror", "aloha_last_error", "aloha_load_isram",
            "aloha_load_tf_rom", "aloha_dma_mem_h2d", "aloha_dma_mem_d2h", "aloha_dma_ksk_h2d",
+           "aloha_dma_mem_h2d_async", "aloha_dma_mem_d2h_async",
            "aloha_spm_written", "aloha_run_vp", "aloha_run_vp_batch", "aloha_run_vp_multi", "aloha_sync",
            "aloha_spm_device_ptr", "aloha_ksk_device_ptr", "aloha_spm_mark_written", "aloha_set_stream",
            "aloha_get_stats", "aloha_get_csr", "aloha_decode", "aloha_host_create",
@@ -93,6 +94,8 @@ def load_library(rebuild: bool = False) -> C.CDLL:
         "aloha_dma_mem_h2d": (C.c_int, [vp, u32, vp, u64]),
         "aloha_dma_mem_d2h": (C.c_int, [vp, vp, u32, u64]),
         "aloha_dma_ksk_h2d": (C.c_int, [vp, u32, vp, u64]),
+        "aloha_dma_mem_h2d_async": (C.c_int, [vp, u32, vp, u64]),
+        "aloha_dma_mem_d2h_async": (C.c_int, [vp, vp, u32, u64]),
         "aloha_spm_written": (C.c_int, [vp, u32, u64, p8]),
         "aloha_run_vp": (C.c_int, [vp, u32, u32, u32, u32, u32, u32]),
         "aloha_run_vp_batch": (C.c_int, [vp, u32, u32, C.POINTER(VpArgs)]),
@@ -198,6 +201,13 @@ class Engine:
             ptr = out if isinstance(out, int) else out.ctypes.data
         self._ck(self.L.aloha_dma_mem_d2h(self.h, ptr, spm_row, nwords * 8), "dma_mem_d2h")
         return out
+
+    def dma_mem_h2d_async(self, spm_row: int, host_ptr: int, nbytes: int):
+        """host_ptr: address of a page-locked buffer that stays valid until sync()."""
+        self._ck(self.L.aloha_dma_mem_h2d_async(self.h, spm_row, host_ptr, nbytes), "dma_mem_h2d_async")
+
+    def dma_mem_d2h_async(self, host_ptr: int, spm_row: int, nbytes: int):
+        self._ck(self.L.aloha_dma_mem_d2h_async(self.h, host_ptr, spm_row, nbytes), "dma_mem_d2h_async")
 
     def dma_ksk_h2d(self, ksk_row: int, data: np.ndarray):
         data = np.ascontiguousarray(data, dtype=np.uint64)

@@ -748,6 +748,22 @@ void commit(aloha *E, const Plan &plan) {
     E->stats.ops_fused += plan.fused;
 }
 
+// Work about to be queued on `st` writes SPM words [off, off+n): it must not overtake a pending
+// asynchronous download of overlapping rows.
+int wait_for_downloads(aloha *E, cudaStream_t st, u64 off, u64 n) {
+    for (size_t i = 0; i < E->pending_down.size();) {
+        auto &p = E->pending_down[i];
+        if (cudaEventQuery(p.done) == cudaSuccess) {
+            cudaEventDestroy(p.done);
+            E->pending_down.erase(E->pending_down.begin() + i);
+            continue;
+        }
+        if (p.off < off + n && off < p.off + p.n) CU(cudaStreamWaitEvent(st, p.done, 0));
+        ++i;
+    }
+    return ALOHA_OK;
+}
+
 std::string plan_key(const aloha *E, const uint32_t *pcs, bool same_pc, uint32_t count, const aloha_vp_args *args) {
     std::string k;
     auto put = [&](const void *p, size_t n) { k.append((const char *)p, n); };
@@ -818,6 +834,11 @@ int run_batch(aloha *E, const uint32_t *pcs, bool same_pc, uint32_t count, const
     } else {
         ++E->stats.plans_reused;
     }
+    if (!E->pending_down.empty())
+        for (auto &w : hit->written) {
+            int rc = wait_for_downloads(E, E->stream, w.first, w.second);
+            if (rc) return rc;
+        }
     int rc = execute_plan(E, *hit);
     if (rc) return rc;
     commit(E, *hit);
@@ -918,6 +939,9 @@ void aloha_destroy(aloha_t *E) {
     cudaFree(E->d_ksk);
     cudaFree(E->d_pool);
     if (E->own_stream) cudaStreamDestroy(E->own_stream);
+    if (E->up_stream) { cudaStreamSynchronize(E->up_stream); cudaStreamDestroy(E->up_stream); }
+    if (E->down_stream) { cudaStreamSynchronize(E->down_stream); cudaStreamDestroy(E->down_stream); }
+    for (auto &p : E->pending_down) cudaEventDestroy(p.done);
     delete E;
 }
 
@@ -948,8 +972,61 @@ int aloha_dma_mem_h2d(aloha_t *E, uint32_t row, const uint64_t *src, uint64_t by
     if (off + n > E->spm_words) return fail(E, ALOHA_E_RANGE, "DMA beyond SPM");
     int rc = cow_for_host_write(E, off, n);
     if (rc) return rc;
+    if (!E->pending_down.empty() && (rc = wait_for_downloads(E, E->stream, off, n))) return rc;
     CU(cudaMemcpyAsync(E->d_spm + off, src, bytes, cudaMemcpyHostToDevice, E->stream));
     mark_written(E, off, n);
+    return ALOHA_OK;
+}
+
+int aloha_dma_mem_h2d_async(aloha_t *E, uint32_t row, const uint64_t *src, uint64_t bytes) {
+    if (!E || !src || bytes % 64) return ALOHA_E_ARG;
+    const u64 off = (u64)row * kLanes, n = bytes / 8;
+    if (off + n > E->spm_words) return fail(E, ALOHA_E_RANGE, "DMA beyond SPM");
+    int rc = cow_for_host_write(E, off, n);
+    if (rc) return rc;
+    if (!E->up_stream) {
+        CU(cudaStreamCreateWithFlags(&E->up_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&E->down_stream, cudaStreamNonBlocking));
+    }
+    // the upload must not overtake kernels already queued (they may still read these rows) ...
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, E->stream));
+    CU(cudaStreamWaitEvent(E->up_stream, ev, 0));
+    CU(cudaEventDestroy(ev));
+    // ... nor a pending download of overlapping rows
+    rc = wait_for_downloads(E, E->up_stream, off, n);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(E->d_spm + off, src, bytes, cudaMemcpyHostToDevice, E->up_stream));
+    // every later run_vp sees the data
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, E->up_stream));
+    CU(cudaStreamWaitEvent(E->stream, ev, 0));
+    CU(cudaEventDestroy(ev));
+    mark_written(E, off, n);
+    return ALOHA_OK;
+}
+
+int aloha_dma_mem_d2h_async(aloha_t *E, uint64_t *dst, uint32_t row, uint64_t bytes) {
+    if (!E || !dst || bytes % 64) return ALOHA_E_ARG;
+    const u64 off = (u64)row * kLanes, n = bytes / 8;
+    if (off + n > E->spm_words) return fail(E, ALOHA_E_RANGE, "DMA beyond SPM");
+    if (!E->up_stream) {
+        CU(cudaStreamCreateWithFlags(&E->up_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&E->down_stream, cudaStreamNonBlocking));
+    }
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, E->stream));                // sees every run_vp issued so far
+    CU(cudaStreamWaitEvent(E->down_stream, ev, 0));
+    CU(cudaEventDestroy(ev));
+    CU(cudaMemcpyAsync(dst, E->d_spm + off, bytes, cudaMemcpyDeviceToHost, E->down_stream));
+    aloha::PendingDma p{off, n, nullptr};
+    CU(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
+    CU(cudaEventRecord(p.done, E->down_stream));
+    // later work that WRITES these rows waits for this event (wait_for_downloads); everything else
+    // keeps running beside the copy
+    E->pending_down.push_back(p);
     return ALOHA_OK;
 }
 
@@ -1013,6 +1090,12 @@ int aloha_run_vp_multi(aloha_t *E, uint32_t count, const uint32_t *pcs, const al
 int aloha_sync(aloha_t *E) {
     if (!E) return ALOHA_E_ARG;
     CU(cudaStreamSynchronize(E->stream));
+    if (E->up_stream) {
+        CU(cudaStreamSynchronize(E->up_stream));
+        CU(cudaStreamSynchronize(E->down_stream));
+    }
+    for (auto &p : E->pending_down) cudaEventDestroy(p.done);
+    E->pending_down.clear();
     return ALOHA_OK;
 }
 

@@ -95,6 +95,9 @@ struct aloha {
     unsigned kbits = 0;
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;   // asynchronous DMA channels
+    struct PendingDma { alb::u64 off, n; cudaEvent_t done; };
+    std::vector<PendingDma> pending_down;                      // downloads not yet known complete
     alb::u64 *d_spm = nullptr, *d_ksk = nullptr, *d_pool = nullptr;
     alb::u64 spm_words = 0, ksk_words = 0;
     uint32_t pool_count = 0;

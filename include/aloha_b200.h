@@ -13,6 +13,7 @@
  *                                                                     src/vp/vxu/vxu_lane.sv:210-218
  *   aloha_dma_mem_h2d              DMA_CMD_MEM read channel           sim/top/top_noaxilite_tb.sv:450-472; src/mem_buf/axi_data_rd_top.sv:58-99
  *   aloha_dma_mem_d2h              DMA write channel                  sim/top/top_noaxilite_tb.sv:474-520
+ *   aloha_dma_mem_*_async          the same two channels, free-running beside the VP as in the RTL
  *   aloha_dma_ksk_h2d              DMA_CMD_KSK                        sim/top/top_noaxilite_tb.sv:372-394
  *   aloha_run_vp                   CSR writes + vp_start + poll done  sim/top/top_noaxilite_tb.sv:396-417;
  *                                                                     src/top/h2_top_no_axilite.sv:145-182; src/mem_buf/axil_parse.sv:50-72
@@ -106,6 +107,15 @@ int aloha_load_tf_rom(aloha_t *, const uint64_t *q, const uint64_t *psi, uint32_
 int aloha_dma_mem_h2d(aloha_t *, uint32_t spm_row, const uint64_t *src, uint64_t bytes);
 int aloha_dma_mem_d2h(aloha_t *, uint64_t *dst, uint32_t spm_row, uint64_t bytes);
 int aloha_dma_ksk_h2d(aloha_t *, uint32_t ksk_row, const uint64_t *src, uint64_t bytes);
+/* Asynchronous DMA: the reference's DMA engine is a block of its own next to the VP
+ * (src/mem_buf/axi_data_rd_top.sv, axi_data_wr_top.sv); these run the copy on dedicated upload /
+ * download streams so transfers in both directions overlap each other and the kernels.  Ordering is
+ * the hardware's: an upload is visible to every run_vp issued after the call; a download sees every
+ * run_vp issued before it; an upload never overtakes earlier work that touches the same rows.
+ * Host buffers must be page-locked for the copies to be truly asynchronous and must stay valid until
+ * aloha_sync (which also waits for both DMA streams). */
+int aloha_dma_mem_h2d_async(aloha_t *, uint32_t spm_row, const uint64_t *src, uint64_t bytes);
+int aloha_dma_mem_d2h_async(aloha_t *, uint64_t *dst, uint32_t spm_row, uint64_t bytes);
 /* out[i] = 1 iff SPM word spm_row*128 + i has ever been written (the 'x' lines of the RTL dumps) */
 int aloha_spm_written(aloha_t *, uint32_t spm_row, uint64_t nwords, uint8_t *out);
 
