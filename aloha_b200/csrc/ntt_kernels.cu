@@ -18,8 +18,8 @@
 // live in [0, 16q) (q < 2^60) and are reduced to canonical form once, at the very end.
 // Inputs are taken as they are (no pre-reduction): the RTL conditionally subtracts q once, which
 // maps [q, 2q) onto the same residue class, and the final canonical reduction makes the stored word
-// identical for every input below 2q.  Forward bounds: 2q -> (+2q per stage) -> 10q -> csub 8q ->
-// 16q | 8q -> 16q -> 8q -> 16q -> canonical.
+// identical for every input below 2q.  Forward bounds: +2q per stage from 2q; only the UPPER input of a
+// butterfly is ever reduced (8q conditional subtract), and only when the stage would pass 16q.
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -59,11 +59,40 @@ __device__ __forceinline__ void gs_bf(u64 &x, u64 &y, const Tw &t, u64 nq, u64 q
     y = mul_shoup(d, t.w, t.wp, nq);
 }
 
+// Bound (units of q) of what the forward column pass stores for S1 column stages: start at 2, +2 per
+// stage, an upper-input reduction to 8 whenever the next stage would pass 16.
+__host__ __device__ constexpr int cols_out_bound(int s1) {
+    int b = 2;
+    for (int s = 0; s < s1; ++s) b = (b + 2 > 16 ? 8 : b) + 2;
+    return b;
+}
+
 }  // namespace
 
 // ============================================================================ forward: columns
 // S1 = number of column stages (R = 2^S1 rows).  LA = min(S1,4) stages in phase A on rows
 // r = h + H k (H = R / 2^LA), LB = S1 - LA stages in phase B on rows 16 G + e.
+//
+// Bound bookkeeping (units of q, resolved at compile time after unrolling): every value entering a
+// stage is < B q; both outputs are < (B_x + 2) q where B_x bounds the UPPER input only -- the lower
+// input goes through the Shoup multiply, which accepts any 64-bit word.  So only the upper inputs are
+// ever reduced (one 8q conditional subtract), and only when B + 2 would pass 16.
+#define ALOHA_CT_STAGE(NELEM, HALF, TWIDX)                                           \
+    {                                                                                \
+        const bool red_ = B + 2 > 16;                                                \
+        Tw w_;                                                                       \
+        _Pragma("unroll") for (int e = 0; e < (NELEM); ++e) {                        \
+            if (e & (HALF)) continue;                                                \
+            if ((e & ((HALF)-1)) == 0) {                                             \
+                const int g0 = e & ~(2 * (HALF)-1);                                  \
+                w_ = ldtw(tw + (TWIDX));                                             \
+            }                                                                        \
+            if (red_) x[e] = csub_s(x[e], q8);                                       \
+            ct_bf(x[e], x[e + (HALF)], w_, nq, q2);                                  \
+        }                                                                            \
+        B = (red_ ? 8 : B) + 2;                                                      \
+    }
+
 template <int S1>
 __global__ void __launch_bounds__(256, COLS_MINB) ntt_fwd_cols(const NttJob *__restrict__ jobs) {
     constexpr int LA = S1 < 4 ? S1 : 4, LB = S1 - LA, E = 1 << LA, R = 1 << S1;
@@ -75,7 +104,7 @@ __global__ void __launch_bounds__(256, COLS_MINB) ntt_fwd_cols(const NttJob *__r
     const NttJob &job = jobs[blockIdx.x / TILES];
     const int c0 = (blockIdx.x % TILES) * W;
     const int t = threadIdx.x, c = t % W, hg = t / W;
-    const u64 q = job.mc.q, q2 = 2 * q, nq = 0 - q;
+    const u64 q = job.mc.q, q2 = 2 * q, q8 = 8 * q, nq = 0 - q;
     const u64 *src = job.src + c0 + c;
     u64 *dst = job.dst + c0 + c;
     const Tw *tw = job.tw;
@@ -83,46 +112,26 @@ __global__ void __launch_bounds__(256, COLS_MINB) ntt_fwd_cols(const NttJob *__r
     u64 x[E];
 #pragma unroll
     for (int k = 0; k < E; ++k) x[k] = src[(size_t)(hg + H * k) * 256];   // < 2q (see header)
-
+    int B = 2;
     // phase A: stage v pairs k-bit (LA-1-v); idx = 2^v + (k >> (LA - v))
 #pragma unroll
-    for (int v = 0; v < LA; ++v) {
-        const int half = E >> (v + 1);
-Tw w;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            if (e & half) continue;
-            if ((e & (half - 1)) == 0) w = ldtw(tw + (1 << v) + ((e & ~(2 * half - 1)) >> (LA - v)));
-            ct_bf(x[e], x[e + half], w, nq, q2);
-        }
-    }
+    for (int v = 0; v < LA; ++v) ALOHA_CT_STAGE(E, E >> (v + 1), (1 << v) + (g0 >> (LA - v)))
     if (LB == 0) {
 #pragma unroll
-        for (int k = 0; k < E; ++k) dst[(size_t)(hg + H * k) * 256] = x[k];  // < 2q + 2q*LA <= 10q
+        for (int k = 0; k < E; ++k) dst[(size_t)(hg + H * k) * 256] = x[k];
         return;
     }
     // exchange: rows h + H k  ->  rows 16 G + e
-    const u64 q8 = 8 * q;
 #pragma unroll
-    for (int k = 0; k < E; ++k) smem[(hg + H * k) * W + c] = csub_s(x[k], q8);  // 10q -> < 8q
+    for (int k = 0; k < E; ++k) smem[(hg + H * k) * W + c] = x[k];
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < E; ++e) x[e] = smem[(16 * hg + e) * W + c];
     // phase B: stage s = 4 + v pairs e-bit (LB-1-v); idx = 2^s + ((16 G + e) >> (S1 - s))
 #pragma unroll
-    for (int v = 0; v < LB; ++v) {
-        const int s = 4 + v;
-        const int half = 1 << (LB - 1 - v);
-Tw w;
+    for (int v = 0; v < LB; ++v) ALOHA_CT_STAGE(E, 1 << (LB - 1 - v), (1 << (4 + v)) + ((16 * hg + g0) >> (S1 - 4 - v)))
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            if (e & half) continue;
-            if ((e & (half - 1)) == 0) w = ldtw(tw + (1 << s) + ((16 * hg + (e & ~(2 * half - 1))) >> (S1 - s)));
-            ct_bf(x[e], x[e + half], w, nq, q2);
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < E; ++e) dst[(size_t)(16 * hg + e) * 256] = x[e];  // < 8q + 2q*LB <= 16q
+    for (int e = 0; e < E; ++e) dst[(size_t)(16 * hg + e) * 256] = x[e];   // < cols_out_bound(S1) q
 }
 
 // ============================================================================ forward: rows
@@ -149,28 +158,15 @@ __global__ void __launch_bounds__(256, ROWS_MINB) ntt_fwd_rows(const NttJob *__r
     const u32 rr = R + r;
 
     u64 x[16];
-    if (S1 == 0) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = src[h + 16 * k];             // < 2q
-    } else {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = csub_s(src[h + 16 * k], q8);  // < 16q -> < 8q
-    }
+    for (int k = 0; k < 16; ++k) x[k] = src[h + 16 * k];
+    int B = cols_out_bound(S1);          // what the column pass left (2 for a bare 256-point transform)
     // phase A: u = 0..3 pairs k-bit (3-u); idx = 2^u (R + r) + (k >> (4 - u))
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int half = 8 >> u;
-Tw w;
+    for (int u = 0; u < 4; ++u) ALOHA_CT_STAGE(16, 8 >> u, (rr << u) + (g0 >> (4 - u)))
+    // exchange h + 16k -> 16g + e
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            if (e & half) continue;
-            if ((e & (half - 1)) == 0) w = ldtw(tw + (rr << u) + ((e & ~(2 * half - 1)) >> (4 - u)));
-            ct_bf(x[e], x[e + half], w, nq, q2);
-        }
-    }
-    // exchange h + 16k -> 16g + e   (values < 16q -> < 8q)
-#pragma unroll
-    for (int k = 0; k < 16; ++k) buf[h + 18 * k] = csub_s(x[k], q8);
+    for (int k = 0; k < 16; ++k) buf[h + 18 * k] = x[k];
     __syncwarp();
 #pragma unroll
     for (int e = 0; e < 16; e += 2) {
@@ -180,16 +176,7 @@ Tw w;
     }
     // phase B: u = 4..7 pairs e-bit (7-u); idx = 2^u (R + r) + ((16 g + e) >> (8 - u))
 #pragma unroll
-    for (int u = 4; u < 8; ++u) {
-        const int half = 128 >> u;
-Tw w;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            if (e & half) continue;
-            if ((e & (half - 1)) == 0) w = ldtw(tw + (rr << u) + ((16 * h + (e & ~(2 * half - 1))) >> (8 - u)));
-            ct_bf(x[e], x[e + half], w, nq, q2);
-        }
-    }
+    for (int u = 4; u < 8; ++u) ALOHA_CT_STAGE(16, 128 >> u, (rr << u) + ((16 * h + g0) >> (8 - u)))
     // < 16q -> canonical; store the thread's 128 contiguous bytes
     const u32 mest = job.mc.mest;
 #pragma unroll
@@ -199,117 +186,6 @@ Tw w;
         v.y = reduce_full(x[e + 1], q, nq, mest);
         *reinterpret_cast<ulonglong2 *>(dst + 16 * h + e) = v;
     }
-}
-
-// ---------------------------------------------------------------------------- pipelined rows
-// Persistent variant of ntt_fwd_rows: every half-warp is an independent worker that walks over rows
-// (grid-stride), double-buffering them in shared memory with cp.async so the next row streams in
-// from HBM/L2 while the current one is in the butterflies.  Results leave through the same buffer
-// as fully coalesced 16-byte stores.  No block-level barrier anywhere.
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int S1>
-__global__ void __launch_bounds__(256, ROWS_MINB) ntt_fwd_rows_pipe(const NttJob *__restrict__ jobs, u32 total_rows) {
-    constexpr int R = 1 << S1;
-    extern __shared__ __align__(16) u64 smem[];          // [16 half-warps][2 buffers][kRowPad]
-    const int t = threadIdx.x, hw = t >> 4, h = t & 15;
-    u64 *buf0 = smem + hw * 2 * kRowPad;
-    const u32 stride = gridDim.x * 16;
-    u32 grow = blockIdx.x * 16 + hw;
-
-    auto row_src = [&](u32 g) -> const u64 * {
-        const NttJob &job = jobs[g / R];
-        return (S1 == 0 ? job.src : job.dst) + (size_t)(g % R) * 256;
-    };
-    // chunk c (16 bytes = words 2c, 2c+1) of the row lands at padded word 2c + 2*(c >> 3)
-    auto prefetch = [&](u32 g, u64 *buf) {
-        if (g < total_rows) {
-            const u64 *src = row_src(g);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int c = h + 16 * i;
-                cp_async16(buf + 2 * c + 2 * (c >> 3), src + 2 * c);
-            }
-        }
-        cp_async_commit();
-    };
-
-    prefetch(grow, buf0);
-    for (int it = 0; grow < total_rows; grow += stride, ++it) {
-        u64 *buf = buf0 + (it & 1) * kRowPad;
-        prefetch(grow + stride, buf0 + ((it + 1) & 1) * kRowPad);
-        const NttJob &job = jobs[grow / R];
-        const u32 r = grow % R;
-        const u64 q = job.mc.q, q2 = 2 * q, q8 = 8 * q, nq = 0 - q;
-        const Tw *tw = job.tw;
-        const u32 rr = R + r;
-        cp_async_wait<1>();
-        __syncwarp();
-
-        u64 x[16];
-        if (S1 == 0) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) x[k] = buf[h + 18 * k];
-        } else {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) x[k] = csub_s(buf[h + 18 * k], q8);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int half = 8 >> u;
-            Tw w;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                if (e & half) continue;
-                if ((e & (half - 1)) == 0) w = ldtw(tw + (rr << u) + ((e & ~(2 * half - 1)) >> (4 - u)));
-                ct_bf(x[e], x[e + half], w, nq, q2);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 16; ++k) buf[h + 18 * k] = csub_s(x[k], q8);   // same words this lane read
-        __syncwarp();
-#pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(buf + 18 * h + e);
-            x[e] = v.x;
-            x[e + 1] = v.y;
-        }
-#pragma unroll
-        for (int u = 4; u < 8; ++u) {
-            const int half = 128 >> u;
-            Tw w;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                if (e & half) continue;
-                if ((e & (half - 1)) == 0) w = ldtw(tw + (rr << u) + ((16 * h + (e & ~(2 * half - 1))) >> (8 - u)));
-                ct_bf(x[e], x[e + half], w, nq, q2);
-            }
-        }
-        const u32 mest = job.mc.mest;
-#pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-            ulonglong2 v;
-            v.x = reduce_full(x[e], q, nq, mest);
-            v.y = reduce_full(x[e + 1], q, nq, mest);
-            *reinterpret_cast<ulonglong2 *>(buf + 18 * h + e) = v;          // same words this lane read
-        }
-        __syncwarp();
-        u64 *dst = job.dst + (size_t)r * 256;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = h + 16 * i;
-            *reinterpret_cast<ulonglong2 *>(dst + 2 * c) =
-                *reinterpret_cast<const ulonglong2 *>(buf + 2 * c + 2 * (c >> 3));
-        }
-        __syncwarp();   // the buffer is refilled by the prefetch issued at the top of the next iteration
-    }
-    cp_async_wait<0>();
 }
 
 // ============================================================================ inverse: rows
@@ -454,13 +330,6 @@ Tw w;
 }
 
 // ============================================================================ launchers
-// Tunables (read once from the environment: A/B switches for profiling runs).
-static int env_int(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
-static const int g_rows_pipe = env_int("ALOHA_ROWS_PIPE", 0);
-static const int g_persistent_ctas = env_int("ALOHA_PERSISTENT_CTAS", 148 * 3);
 unsigned long long g_launches = 0;
 unsigned long long kernel_launch_count() { return g_launches; }
 static inline void count_launch() { ++g_launches; }
@@ -475,19 +344,7 @@ static cudaError_t fwd_impl(const NttJob *jobs, u32 njobs, cudaStream_t st) {
         count_launch();
     }
     const u32 rows = njobs * R;
-    if (g_rows_pipe) {
-        static bool attr_set = false;
-        constexpr size_t smem = 16 * 2 * kRowPad * 8;
-        if (!attr_set) {
-            cudaFuncSetAttribute(ntt_fwd_rows_pipe<S1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
-        }
-        const u32 tiles = (rows + 15) / 16;
-        const u32 grid = tiles < (u32)g_persistent_ctas ? tiles : (u32)g_persistent_ctas;
-        ntt_fwd_rows_pipe<S1><<<grid, 256, smem, st>>>(jobs, rows);
-    } else {
-        ntt_fwd_rows<S1><<<(rows + 15) / 16, 256, 0, st>>>(jobs, rows);
-    }
+    ntt_fwd_rows<S1><<<(rows + 15) / 16, 256, 0, st>>>(jobs, rows);
     count_launch();
     return cudaGetLastError();
 }

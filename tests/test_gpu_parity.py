@@ -4,6 +4,8 @@
   (2) the oracle (CPU golden model) on seeded synthetic inputs at sizes it finishes in seconds;
   (3) size-independent properties at the BASELINE.json sizes (N = 2^16, 32 limbs).
 Nothing here reads /root/reference."""
+import os
+
 import numpy as np
 import pytest
 
@@ -387,3 +389,34 @@ def test_async_dma_pipeline_equals_blocking_dma():
         want = O.NttTables(n, primes, psis).batch(x.copy(), np.arange(B * L) % L)
         assert (hout.numpy().view(np.uint64).reshape(B * L, n) == want).all(), rep
         assert (eng.dma_mem_d2h(B * per_poly, B * L * n).reshape(B * L, n) == want).all()
+
+
+def test_replay_cli_writes_reference_format_dumps(tmp_path):
+    """python -m aloha_b200.replay on case0_4_4 rebuilt as text files: the dump files it writes parse
+    back to the reference's golden hashes ('x' lines included)."""
+    from aloha_b200 import replay
+    m = G.manifest()
+    n, entry = m["n"], m["cases"]["case0_4_4"]
+    ops, dram, enc, ksk = G.case_inputs("case0_4_4")
+
+    def write(path, arr):
+        with open(path, "w") as f:
+            f.write("\n".join(str(int(v)) for v in arr) + "\n")
+    (tmp_path / "prog.txt").write_text("\n".join(entry["program"]) + "\n")
+    write(tmp_path / "ksk2.txt", ksk[0])
+    args = ["--program", str(tmp_path / "prog.txt"), "--isram", os.path.join(G.GOLDEN, "isram"),
+            "--ksk", f"2:{tmp_path / 'ksk2.txt'}", "--dump-dir", str(tmp_path / "out"), "--cipher"]
+    for i, key in entry["loads"].items():
+        write(tmp_path / f"ct{i}.txt", G.pool(key))
+        args.append(f"{ops[int(i)].dram_addr}:{tmp_path / f'ct{i}.txt'}")
+    args.append("--encoder")
+    for i, data in enc.items():
+        write(tmp_path / f"enc{i}.txt", data)
+        args.append(f"{i}:{tmp_path / f'enc{i}.txt'}")
+    assert replay.main(args) == 0
+    for name, want in entry["dumps"].items():
+        toks = (tmp_path / "out" / (name + ".txt")).read_text().split()
+        assert len(toks) == 4 * n
+        wr = np.array([t != "x" for t in toks])
+        data = np.array([int(t) if t != "x" else 0 for t in toks], dtype=np.uint64)
+        assert G.poly_hashes(data, wr, n) == want, name
