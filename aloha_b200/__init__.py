@@ -313,6 +313,12 @@ class HostDriver:
         if rc:
             raise AlohaError(rc, "set_encoder_output")
 
+    def run_op_nodump(self, i: int):
+        """Run host op i without the testbench's per-op dump read-back (asynchronous)."""
+        rc = self.L.aloha_host_run_op(self.h, i, None, None, None, None, None)
+        if rc:
+            raise AlohaError(rc, f"host_run_op({i})", self.L.aloha_last_error(self.eng.h).decode())
+
     def run_op(self, i: int):
         """-> [(sub_id or None, data[4n], written[4n])] in the order the TB writes its dump files."""
         w = 4 * self.n

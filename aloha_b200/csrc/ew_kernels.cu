@@ -157,11 +157,29 @@ __global__ void __launch_bounds__(kThreads) sop_kernel(const SopJob *__restrict_
     const u64 q = job.q, iq = job.iq;
     const u32 i = (blockIdx.x * kThreads + threadIdx.x) * kVec;
     if (i >= n) return;
+    const ulonglong2 *pairs = reinterpret_cast<const ulonglong2 *>(job.pairs);
     u64 acc0 = 0, acc1 = 0;
-    for (u32 t = 0; t < job.terms; ++t) {
-        const ulonglong2 pp = __ldg(reinterpret_cast<const ulonglong2 *>(job.pairs) + t);
-        const u64 *pa = reinterpret_cast<const u64 *>(pp.x), *pb = reinterpret_cast<const u64 *>(pp.y);
-        const ulonglong2 a = ld2(pa + i), b = ld2(pb + i);
+    constexpr u32 kU = 4;                       // operand pairs in flight per thread
+    u32 t = 0;
+    for (; t + kU <= job.terms; t += kU) {
+        ulonglong2 a[kU], b[kU];
+#pragma unroll
+        for (u32 u = 0; u < kU; ++u) {
+            const ulonglong2 pp = __ldg(pairs + t + u);
+            a[u] = ld2(reinterpret_cast<const u64 *>(pp.x) + i);
+            b[u] = ld2(reinterpret_cast<const u64 *>(pp.y) + i);
+        }
+#pragma unroll
+        for (u32 u = 0; u < kU; ++u) {
+            const u64 m0 = rtl_alu<ALU_MUL_VV>(a[u].x, b[u].x, 0, q, iq);
+            const u64 m1 = rtl_alu<ALU_MUL_VV>(a[u].y, b[u].y, 0, q, iq);
+            if (t + u == 0) { acc0 = m0; acc1 = m1; }
+            else { acc0 = rtl_alu<ALU_ADD_VV>(acc0, m0, 0, q, iq); acc1 = rtl_alu<ALU_ADD_VV>(acc1, m1, 0, q, iq); }
+        }
+    }
+    for (; t < job.terms; ++t) {
+        const ulonglong2 pp = __ldg(pairs + t);
+        const ulonglong2 a = ld2(reinterpret_cast<const u64 *>(pp.x) + i), b = ld2(reinterpret_cast<const u64 *>(pp.y) + i);
         const u64 m0 = rtl_alu<ALU_MUL_VV>(a.x, b.x, 0, q, iq);
         const u64 m1 = rtl_alu<ALU_MUL_VV>(a.y, b.y, 0, q, iq);
         if (t == 0) { acc0 = m0; acc1 = m1; }

@@ -159,7 +159,8 @@ int aloha_host_dram_read(aloha_host_t *, uint64_t byte_addr, void *dst, uint64_t
 int aloha_host_set_encoder_output(aloha_host_t *, uint32_t op_index, const uint64_t *data,
                                   uint64_t nwords);
 /* Runs op `op_index` and produces its dump(s): dump / written get 4n entries (inst_<i>_out.txt);
- * for encode ops sub_dump / sub_written get the 4n entries of inst_<i>_0_out.txt and *has_sub = 1. */
+ * for encode ops sub_dump / sub_written get the 4n entries of inst_<i>_0_out.txt and *has_sub = 1.
+ * dump == NULL runs the op without the read-back (nothing is copied to the host, nothing blocks). */
 int aloha_host_run_op(aloha_host_t *, uint32_t op_index, uint64_t *dump, uint8_t *written,
                       uint64_t *sub_dump, uint8_t *sub_written, int *has_sub);
 /* "%0d" per line, 'x' for never-written words (dump_poly, top_noaxilite_tb.sv:536-565) */
