@@ -116,22 +116,22 @@ __global__ void __launch_bounds__(256, COLS_MINB) ntt_fwd_cols(const NttJob *__r
     // phase A: stage v pairs k-bit (LA-1-v); idx = 2^v + (k >> (LA - v))
 #pragma unroll
     for (int v = 0; v < LA; ++v) ALOHA_CT_STAGE(E, E >> (v + 1), (1 << v) + (g0 >> (LA - v)))
-    if (LB == 0) {
+    if constexpr (LB == 0) {
 #pragma unroll
         for (int k = 0; k < E; ++k) dst[(size_t)(hg + H * k) * 256] = x[k];
-        return;
+    } else {
+        // exchange: rows h + H k  ->  rows 16 G + e
+#pragma unroll
+        for (int k = 0; k < E; ++k) smem[(hg + H * k) * W + c] = x[k];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < E; ++e) x[e] = smem[(16 * hg + e) * W + c];
+        // phase B: stage s = 4 + v pairs e-bit (LB-1-v); idx = 2^s + ((16 G + e) >> (S1 - s))
+#pragma unroll
+        for (int v = 0; v < LB; ++v) ALOHA_CT_STAGE(E, 1 << (LB - 1 - v), (1 << (4 + v)) + ((16 * hg + g0) >> (S1 - 4 - v)))
+#pragma unroll
+        for (int e = 0; e < E; ++e) dst[(size_t)(16 * hg + e) * 256] = x[e];   // < cols_out_bound(S1) q
     }
-    // exchange: rows h + H k  ->  rows 16 G + e
-#pragma unroll
-    for (int k = 0; k < E; ++k) smem[(hg + H * k) * W + c] = x[k];
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < E; ++e) x[e] = smem[(16 * hg + e) * W + c];
-    // phase B: stage s = 4 + v pairs e-bit (LB-1-v); idx = 2^s + ((16 G + e) >> (S1 - s))
-#pragma unroll
-    for (int v = 0; v < LB; ++v) ALOHA_CT_STAGE(E, 1 << (LB - 1 - v), (1 << (4 + v)) + ((16 * hg + g0) >> (S1 - 4 - v)))
-#pragma unroll
-    for (int e = 0; e < E; ++e) dst[(size_t)(16 * hg + e) * 256] = x[e];   // < cols_out_bound(S1) q
 }
 
 // ============================================================================ forward: rows

@@ -51,17 +51,21 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, indices, enabled=True):
+        """One nvidia-smi process for all the job's GPUs (rank 0 only: NVML polling from every rank
+        perturbs the launches it is supposed to observe)."""
+        self.indices, self.rows, self.proc, self.enabled = list(indices), [], None, enabled
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-i", ",".join(str(i) for i in self.indices)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -79,12 +83,17 @@ class ClockSampler:
             self.t.join(timeout=2)
 
     def summary(self):
-        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = [r for r in self.rows if len(r) >= 7 and r[1].isdigit()]
+        sm = [int(r[1]) for r in rows]
+        mx = [int(r[2]) for r in rows if r[2].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
-        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[3 + i] == "Active"})
+        out = {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": reasons, "samples": len(sm)}
+        if len(self.indices) > 1:
+            out["sm_mhz_min_per_gpu"] = {g: min(int(r[1]) for r in rows if r[0] == str(g)) for g in self.indices
+                                         if any(r[0] == str(g) for r in rows)}
+        return out
 
 
 def workload_params():
@@ -233,6 +242,9 @@ def run_gpu(args):
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
+            allms = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(allms, ms)
+            timed.last_per_rank = [float(t.item()) for t in allms]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
@@ -240,9 +252,10 @@ def run_gpu(args):
     for _ in range(max(args.warmup, 3)):
         step()
     s0 = eng.stats()
-    with ClockSampler(local) as clk:
+    with ClockSampler(range(world), enabled=(rank == 0)) as clk:
         ms = timed(step, args.steps)
     s1 = eng.stats()
+    per_rank_ms = getattr(timed, "last_per_rank", None)
     launches = s1["kernel_launches"] - s0["kernel_launches"]
     ntts_per_step = LIMBS * POLYS
     value = world * ntts_per_step * args.steps / (ms / 1e3)
@@ -333,6 +346,8 @@ def run_gpu(args):
             "intt": {"value": inv_value, "unit": "limb-NTTs/s", "ms_per_step": ms_inv / args.steps},
             "engine_stats": {k: s1[k] - s0[k] for k in s1},
         }
+        if world > 1:
+            line["per_rank"] = {"ms_timed_region": per_rank_ms}
         line.update(extra)
         if world == 1:
             line["cpu_baseline"] = {"value": cpu_all, "unit": "limb-NTTs/s", "cores": cores, "kind": "port",
