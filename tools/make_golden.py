@@ -86,7 +86,12 @@ def load_microcode(model):
         model.load_isram(O.parse_mem_words(open(os.path.join(d, name + ".mem")).read()), pc)
 
 
-def main():
+def main(check_only: bool = False):
+    """check_only: verify the oracle against every reference vector, write nothing."""
+    global OUT
+    if check_only:
+        import tempfile
+        OUT = tempfile.mkdtemp(prefix="aloha_golden_check_")
     os.makedirs(OUT, exist_ok=True)
     pool = Pool()
     manifest = {"n": N, "cases": {}, "kernels": [], "moduli": [[O.Q0, O.PSI0], [O.Q1, O.PSI1],
@@ -232,7 +237,10 @@ def main():
     size = os.path.getsize(os.path.join(OUT, "pool.npz"))
     print(f"checked {checked} reference vectors; pool.npz = {size / 1e6:.1f} MB "
           f"({len(pool.arrays)} arrays)")
+    if check_only:
+        shutil.rmtree(OUT, ignore_errors=True)
+    return checked
 
 
 if __name__ == "__main__":
-    main()
+    main(check_only="--check-only" in sys.argv)
