@@ -32,12 +32,22 @@ def pool(key: str) -> np.ndarray:
 
 def microcode():
     """[(words (n,12) uint8, pc)] for the four shipped kernels."""
-    out = []
-    for name, pc in (("encode_post", O.ISRAM_ENCODE_POST), ("mul_plain", O.ISRAM_MUL_PLAIN),
-                     ("hom_add", O.ISRAM_HOM_ADD), ("keyswitch", O.ISRAM_KEYSWITCH)):
-        text = open(os.path.join(GOLDEN, "isram", name + ".mem")).read()
-        out.append((O.parse_mem_words(text), pc))
-    return out
+    mc = json.load(open(os.path.join(GOLDEN, "microcode.json")))
+    return [(O.parse_mem_words("\n".join(k["words"])), k["pc"]) for k in mc.values()]
+
+
+def microcode_words(name: str):
+    mc = json.load(open(os.path.join(GOLDEN, "microcode.json")))
+    return O.parse_mem_words("\n".join(mc[name]["words"]))
+
+
+def write_microcode_dir(path: str):
+    """Materialise the kernels as <name>.mem files ($readmemh text), as the replay CLI reads them."""
+    os.makedirs(path, exist_ok=True)
+    for name, k in json.load(open(os.path.join(GOLDEN, "microcode.json"))).items():
+        with open(os.path.join(path, name + ".mem"), "w") as f:
+            f.write("\n".join(k["words"]) + "\n")
+    return path
 
 
 def poly_hashes(data: np.ndarray, written: np.ndarray, n: int):

@@ -54,7 +54,7 @@ def test_assembler_reproduces_shipped_microcode_semantics():
     for l, q in enumerate((q0, q1)):
         p.vsetq(q).vle(0, asm.BASE_SRC0, 64 * l).vntt(2, 0).vse(2, asm.BASE_RSLT, 64 * l)
     p.brk()
-    shipped = O.parse_mem_words(open(os.path.join(G.GOLDEN, "isram", "encode_post.mem")).read())
+    shipped = G.microcode_words("encode_post")
     mine = p.words()
     assert len(mine) == len(shipped)
     for a, b in zip(mine, shipped):

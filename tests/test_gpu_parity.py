@@ -404,7 +404,7 @@ def test_replay_cli_writes_reference_format_dumps(tmp_path):
             f.write("\n".join(str(int(v)) for v in arr) + "\n")
     (tmp_path / "prog.txt").write_text("\n".join(entry["program"]) + "\n")
     write(tmp_path / "ksk2.txt", ksk[0])
-    args = ["--program", str(tmp_path / "prog.txt"), "--isram", os.path.join(G.GOLDEN, "isram"),
+    args = ["--program", str(tmp_path / "prog.txt"), "--isram", G.write_microcode_dir(str(tmp_path / "isram")),
             "--ksk", f"2:{tmp_path / 'ksk2.txt'}", "--dump-dir", str(tmp_path / "out"), "--cipher"]
     for i, key in entry["loads"].items():
         write(tmp_path / f"ct{i}.txt", G.pool(key))
@@ -420,3 +420,31 @@ def test_replay_cli_writes_reference_format_dumps(tmp_path):
         wr = np.array([t != "x" for t in toks])
         data = np.array([int(t) if t != "x" else 0 for t in toks], dtype=np.uint64)
         assert G.poly_hashes(data, wr, n) == want, name
+
+
+def test_edge_cases_empty_batch_mixed_vl_and_last_rows():
+    """count = 0 batches, a stream that changes VL midway (ragged polynomial sizes in one plan), and
+    accesses that end exactly at the last SPM row."""
+    primes, psis = synth(1024, 1)
+    q = primes[0]
+    rows = 32
+    eng = A.Engine(vlmax_bits=1024 * 64, spm_rows=rows, ksk_rows=0, moduli=list(zip(primes, psis)))
+    eng.run_vp_batch(0, [])                                   # nothing to do, nothing to fail
+    assert eng.stats()["instructions"] == 0
+    p = asm.Program().vsetvl(256).vsetq(q).vle(0, 0, 0).vntt(2, 0).vse(2, 2, 0)
+    p.vsetvl(1024).vle(1, 0, 8).vntt(3, 1).vse(3, 2, 8).brk()     # second half at N = 1024
+    eng.load_isram(p.words(), 0)
+    rng = np.random.default_rng(8)
+    a, b = rng.integers(0, q, 256, dtype=np.uint64), rng.integers(0, q, 1024, dtype=np.uint64)
+    eng.dma_mem_h2d(0, a)
+    eng.dma_mem_h2d(8, b)
+    eng.run_vp(0, 0, 0, 16)                                   # outputs at rows 16..17 and 24..31 (the last row)
+    psi256, psi1024 = pow(psis[0], 4, q), psis[0]
+    assert (eng.dma_mem_d2h(16, 256) == O.ntt(a, q, psi256)).all()
+    assert (eng.dma_mem_d2h(24, 1024) == O.ntt(b, q, psi1024)).all()
+    assert eng.spm_written(16, 256).all() and not eng.spm_written(18, 6 * 128).any()
+    with pytest.raises(A.AlohaError) as e:                    # one row further is out of range
+        eng.run_vp(0, 0, 0, 17)
+    assert e.value.name == "E_RANGE"
+    with pytest.raises(A.AlohaError):
+        eng.dma_mem_h2d(rows - 1, np.zeros(256, dtype=np.uint64))

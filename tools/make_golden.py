@@ -8,8 +8,8 @@ against EVERY golden vector the reference holds for the hot path, and writes com
                                encoder outputs, kernel-level inputs)
   tests/golden/manifest.json   programs, which pool array feeds what, and the sha256 of every
                                expected output polynomial (+ which polys are all-'x')
-  tests/golden/isram/*.mem     the four microcode kernels (the R-type instruction streams that are
-                               the path's input format)
+  tests/golden/microcode.json  the four microcode kernels as lists of 96-bit words (the R-type
+                               instruction streams that are the path's input format) + their ROM pcs
   tests/golden/decode/*.json   sequencer decode goldens (instruction words + 17 expected fields)
 
 Expected outputs are stored as hashes, not data: a mismatch is diagnosed per polynomial, and the
@@ -99,11 +99,11 @@ def main(check_only: bool = False):
     checked = 0
 
     # ---- microcode + decode goldens -------------------------------------------------------
-    os.makedirs(os.path.join(OUT, "isram"), exist_ok=True)
-    for name in ("encode_post", "mul_plain", "hom_add", "keyswitch"):
-        shutil.copyfile(os.path.join(REF, "sim/vp/isram_file_generator", name + ".mem"),
-                        os.path.join(OUT, "isram", name + ".mem"))
-        os.chmod(os.path.join(OUT, "isram", name + ".mem"), 0o644)
+    microcode = {}
+    for name, pc in (("encode_post", 0), ("mul_plain", 64), ("hom_add", 160), ("keyswitch", 256)):
+        words = open(os.path.join(REF, "sim/vp/isram_file_generator", name + ".mem")).read().split()
+        microcode[name] = {"pc": pc, "source": f"sim/vp/isram_file_generator/{name}.mem", "words": words}
+    json.dump(microcode, open(os.path.join(OUT, "microcode.json"), "w"), indent=0)
     os.makedirs(os.path.join(OUT, "decode"), exist_ok=True)
     for mem, gold in (("add_inst", "homo_add"), ("mul_inst", "mul_plain"),
                       ("inst_issue_test", "inst_issue_test")):
