@@ -52,19 +52,20 @@ def peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,clocks.mem")
 
-    def __init__(self, indices, enabled=True):
+    def __init__(self, indices, enabled=True, period_ms=200):
         """One nvidia-smi process for all the job's GPUs (rank 0 only: NVML polling from every rank
         perturbs the launches it is supposed to observe)."""
         self.indices, self.rows, self.proc, self.enabled = list(indices), [], None, enabled
+        self.period_ms = period_ms
 
     def __enter__(self):
         if not self.enabled:
             return self
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms),
                  "-i", ",".join(str(i) for i in self.indices)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -90,6 +91,12 @@ class ClockSampler:
         reasons = sorted({names[i] for r in rows for i in range(4) if r[3 + i] == "Active"})
         out = {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                "reasons": reasons, "samples": len(sm)}
+        try:
+            pw = [float(r[7]) for r in rows if len(r) > 7]
+            out["power_w_max"] = max(pw) if pw else None
+            out["mem_mhz_min"] = min(int(r[8]) for r in rows if len(r) > 8 and r[8].isdigit())
+        except Exception:
+            pass
         if len(self.indices) > 1:
             out["sm_mhz_min_per_gpu"] = {g: min(int(r[1]) for r in rows if r[0] == str(g)) for g in self.indices
                                          if any(r[0] == str(g) for r in rows)}
@@ -249,10 +256,23 @@ def run_gpu(args):
         return float(ms.item())
 
     step = lambda: eng.run_vp_batch(0, calls)
-    for _ in range(max(args.warmup, 3)):
-        step()
-    s0 = eng.stats()
-    with ClockSampler(range(world), enabled=(rank == 0)) as clk:
+    # Warm-up: at least W (>= 3) steps, and enough of them to keep every GPU busy for ~0.4 s -- with
+    # several GPUs starting from idle at once the SM clocks need tens of milliseconds to ramp up under
+    # the node's power management, and a 30 ms timed region would otherwise measure the ramp.  The
+    # clock sampler runs from the start of the warm-up to the end of the timed region.
+    with ClockSampler(range(world), enabled=(rank == 0 and not os.environ.get("ALOHA_BENCH_NO_SAMPLER")),
+                      period_ms=200) as clk:
+        n_warm = max(args.warmup, 3)
+        t0 = time.perf_counter()
+        for _ in range(n_warm):
+            step()
+        torch.cuda.synchronize()
+        per_step = max((time.perf_counter() - t0) / n_warm, 1e-4)
+        extra_warm = max(0, int(0.4 / per_step) - n_warm)
+        for _ in range(extra_warm):
+            step()
+        n_warm += extra_warm
+        s0 = eng.stats()
         ms = timed(step, args.steps)
     s1 = eng.stats()
     per_rank_ms = getattr(timed, "last_per_rank", None)
@@ -327,7 +347,7 @@ def run_gpu(args):
             traffic = None
         line = {
             "metric": "limb_ntts_per_s_n65536", "value": value, "unit": "limb-NTTs/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "steps": args.steps, "warmup": n_warm, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "config": workload_config(),
             "clocks": clk.summary(),
@@ -429,10 +449,12 @@ def measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, polys
     k = pow(3, N // 4, 2 * N)                                                  # a Galois element >= N
     calls = A.Engine.make_args([(b * per_poly, polys * per_poly + 2 * b * per_poly, 3 * polys * per_poly + b * per_poly,
                                  0, k) for b in range(polys)])
-    for _ in range(3):
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 0.3:
         eng.run_vp_batch(0, calls)
+        torch.cuda.synchronize()
     s0 = eng.stats()
-    steps = 10
+    steps = 20
     ms = timed(lambda: eng.run_vp_batch(0, calls), steps)
     s1 = eng.stats()
     per_s = LIMBS * polys * steps / (ms / 1e3)
@@ -472,8 +494,13 @@ def measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank, L=
     k = pow(3, 2, 2 * N)
     for _ in range(2):
         ks.run(k)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 0.4:      # clock ramp (see the main warm-up)
+        ks.run(k)
+        torch.cuda.synchronize()
     s0 = eng.stats()
-    steps = 5
+    steps = 20
     ms = timed(lambda: ks.run(k), steps)
     s1 = eng.stats()
     ms_comm = None
