@@ -263,15 +263,15 @@ def run_gpu(args):
     with ClockSampler(range(world), enabled=(rank == 0 and not os.environ.get("ALOHA_BENCH_NO_SAMPLER")),
                       period_ms=200) as clk:
         n_warm = max(args.warmup, 3)
-        t0 = time.perf_counter()
         for _ in range(n_warm):
             step()
         torch.cuda.synchronize()
-        per_step = max((time.perf_counter() - t0) / n_warm, 1e-4)
-        extra_warm = max(0, int(0.4 / per_step) - n_warm)
-        for _ in range(extra_warm):
-            step()
-        n_warm += extra_warm
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < 0.4:
+            for _ in range(8):
+                step()
+            torch.cuda.synchronize()
+            n_warm += 8
         s0 = eng.stats()
         ms = timed(step, args.steps)
     s1 = eng.stats()
@@ -306,7 +306,9 @@ def run_gpu(args):
     # Host buffers -> SPM -> NTT -> host buffers, through the C-ABI only.  The batch is cut into
     # chunks so the upload of chunk c+1, the transform of chunk c and the download of chunk c-1
     # overlap (aloha_dma_mem_*_async = the DMA block running beside the VP).
-    n_chunks = 8 if POLYS % 8 == 0 else 1
+    n_chunks = int(os.environ.get("ALOHA_E2E_CHUNKS", "16"))
+    if POLYS % n_chunks:
+        n_chunks = 1
     cp = POLYS // n_chunks
     chunk_bytes = cp * LIMBS * N * 8
     chunk_calls = [A.Engine.make_args([(b * per_poly, 0, rows + b * per_poly, 0, 0)
