@@ -84,6 +84,7 @@ int get_tables(aloha *E, int mod, unsigned logn, const TwTable **out) {
     t.mc.ninv = a.w; t.mc.ninv_p = a.wp;
     t.mc.wninv = b.w; t.mc.wninv_p = b.wp;
     t.mc.mest = (u32)((((u128)1) << 91) / q);
+    t.mc.pre = 0;
     *out = &(E->tw_tables[key] = t);
     return ALOHA_OK;
 }
@@ -476,6 +477,25 @@ size_t fuse_ops(std::vector<VecOp> &ops, const Loc *final_loc, const aloha *E) {
             break;
         }
     }
+    // VCPY / VFQMOD feeding exactly one forward transform under the same modulus (the key-switch base
+    // extension): the transform applies the op while loading, the intermediate never exists.
+    for (size_t i = 0; i < n; ++i) {
+        VecOp &t = ops[i];
+        if (t.dead || t.kind != K_NTT || t.pre) continue;
+        const int pe = prod_a[i];
+        if (pe < 0 || ops[pe].dead || ops[pe].kind != K_EW || ops[pe].q != t.q || ops[pe].n != t.n) continue;
+        const VecOp &e = ops[pe];
+        const u32 pre = (e.alu == A_ADDVS && e.s == 0) ? (u32)PRE_VCPY : e.alu == A_MOD ? (u32)PRE_VFQMOD : 0u;
+        if (!pre || !single_use_temp(pe)) continue;
+        bool clobbered = false;
+        for (size_t j = pe + 1; j < i && !clobbered; ++j)
+            if (!ops[j].dead && overlap(ops[j].dst, ops[j].n, e.a, e.n)) clobbered = true;
+        if (clobbered) continue;
+        t.pre = pre;
+        t.a = e.a;
+        ops[pe].dead = true;
+        ++fused;
+    }
     // Accumulation chains: acc_t = acc_{t-1} + a_t b_t where acc_{t-1} is itself a single-use, dead
     // product or multiply-add collapse into one sum-of-products op (same evaluation order).
     {
@@ -639,6 +659,7 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
                     int rc = get_tables(E, o.mod, ilog2(o.n), &tw);
                     if (rc) return rc;
                     NttJob nj{o.a, o.dst, o.kind == K_NTT ? tw->fwd : tw->inv, tw->mc};
+                    nj.mc.pre = o.pre;
                     append(tables, nj);
                     break;
                 }

@@ -51,6 +51,7 @@ struct VecOp {
     bool dead = false;                                     // removed by the fusion pass
     std::vector<std::pair<const u64 *, const u64 *>> terms;   // K_SOP: dst = sum_t a_t * b_t (in this order)
     u64 s = 0, q = 0, iq = 0, k = 0, kinv = 0;
+    u32 pre = 0;                                           // K_NTT: base-extension op folded into the load
     int mod = -1;
     int level = 0;
 };

@@ -21,8 +21,9 @@ struct ModulusConsts {
     u64 ninv, ninv_p;      // N^-1 mod q (Shoup pair)            -- inverse transform, last stage
     u64 wninv, wninv_p;    // itw[1] * N^-1 mod q (Shoup pair)
     u32 mest;              // floor(2^91 / q)
-    u32 pad;
+    u32 pre;               // element-wise op folded into the transform's load: 0 none, 1 VCPY, 2 VFQMOD
 };
+enum NttPre : u32 { PRE_NONE = 0, PRE_VCPY = 1, PRE_VFQMOD = 2 };
 
 // One limb-polynomial transform.
 struct NttJob {

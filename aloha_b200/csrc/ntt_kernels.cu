@@ -59,6 +59,20 @@ __device__ __forceinline__ void gs_bf(u64 &x, u64 &y, const Tw &t, u64 nq, u64 q
     y = mul_shoup(d, t.w, t.wp, nq);
 }
 
+// Base-extension primitive folded into the load of a forward transform, word-exact:
+//   VCPY   = addmod(r(x), 0)  -> two compare-based conditional subtracts (expander.v:396-417);
+//   VFQMOD = barrett(r(x), 1) -> x mod q for EVERY 64-bit x (the RTL's quotient estimate is within one
+//            of floor(x/q) for 60-bit q), i.e. exactly what reduce_full computes.
+__device__ __forceinline__ u64 apply_pre(u64 x, u32 pre, u64 q, u64 nq, u32 mest) {
+    if (pre == PRE_VCPY) {
+        x = x >= q ? x - q : x;
+        x = x >= q ? x - q : x;
+    } else if (pre == PRE_VFQMOD) {
+        x = reduce_full(x, q, nq, mest);
+    }
+    return x;
+}
+
 // Bound (units of q) of what the forward column pass stores for S1 column stages: start at 2, +2 per
 // stage, an upper-input reduction to 8 whenever the next stage would pass 16.
 __host__ __device__ constexpr int cols_out_bound(int s1) {
@@ -112,6 +126,10 @@ __global__ void __launch_bounds__(256, COLS_MINB) ntt_fwd_cols(const NttJob *__r
     u64 x[E];
 #pragma unroll
     for (int k = 0; k < E; ++k) x[k] = src[(size_t)(hg + H * k) * 256];   // < 2q (see header)
+    if (job.mc.pre) {
+#pragma unroll
+        for (int k = 0; k < E; ++k) x[k] = apply_pre(x[k], job.mc.pre, q, nq, job.mc.mest);
+    }
     int B = 2;
     // phase A: stage v pairs k-bit (LA-1-v); idx = 2^v + (k >> (LA - v))
 #pragma unroll
@@ -160,6 +178,10 @@ __global__ void __launch_bounds__(256, ROWS_MINB) ntt_fwd_rows(const NttJob *__r
     u64 x[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) x[k] = src[h + 16 * k];
+    if (S1 == 0 && job.mc.pre) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = apply_pre(x[k], job.mc.pre, q, nq, job.mc.mest);
+    }
     int B = cols_out_bound(S1);          // what the column pass left (2 for a bare 256-point transform)
     // phase A: u = 0..3 pairs k-bit (3-u); idx = 2^u (R + r) + (k >> (4 - u))
 #pragma unroll
