@@ -267,7 +267,7 @@ def run_gpu(args):
             step()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        while time.perf_counter() - t0 < 0.4:
+        while not args.quick and time.perf_counter() - t0 < 0.4:   # --quick (profiling): exactly W warm-ups
             for _ in range(8):
                 step()
             torch.cuda.synchronize()
@@ -476,7 +476,8 @@ def measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank, L=
     psi = [params.min_primitive_root(p, 2 * N) for p in q + [P]]
     lay = KS.KeySwitchLayout(N, q, P, world, rank)
     eng = A.Engine(vlmax_bits=N * 64, spm_rows=lay.spm_rows, ksk_rows=lay.ksk_rows,
-                   moduli=list(zip(q + [P], psi)), pool_buffers=6144, isram_depth=32768, **eng_kwargs)
+                   moduli=list(zip(q + [P], psi)), pool_buffers=6144, isram_depth=32768,
+                   flags=int(os.environ.get("ALOHA_BENCH_KS_FLAGS", "0")), **eng_kwargs)
     eng.set_stream(stream.cuda_stream)
     comm = KS.TorchComm() if world > 1 else KS.LocalComm()
     ks = KS.ShardedKeySwitch(eng, lay, comm)
