@@ -51,13 +51,7 @@ __device__ __forceinline__ void ct_bf(u64 &x, u64 &y, const Tw &t, u64 nq, u64 q
     y = (x + x + q2) - xp;
     x = xp;
 }
-// GS butterfly, Harvey: inputs < 2q, outputs < 2q.
-__device__ __forceinline__ void gs_bf(u64 &x, u64 &y, const Tw &t, u64 nq, u64 q2) {
-    const u64 s = x + y;
-    const u64 d = x - y + q2;
-    x = csub_s(s, q2);
-    y = mul_shoup(d, t.w, t.wp, nq);
-}
+
 
 // Base-extension primitive folded into the load of a forward transform, word-exact:
 //   VCPY   = addmod(r(x), 0)  -> two compare-based conditional subtracts (expander.v:396-417);
@@ -212,6 +206,55 @@ __global__ void __launch_bounds__(256, ROWS_MINB) ntt_fwd_rows(const NttJob *__r
 
 // ============================================================================ inverse: rows
 // GS stages lt = 0..7 (gap 2^lt).  idx = (N >> (lt+1)) + (j >> (lt+1)),  j = r*256 + jj.
+//
+// Lazy sums: out_x = x + y (bound b_x + b_y), out_y = (x - y + b_y q) * w (bound 2).  bnd[] carries the
+// per-register bounds (units of q) through the unrolled stages at compile time; an input is reduced
+// (8q conditional subtract) only when b_x + b_y would pass 16, and a block ends by bringing every
+// register back under 2q -- 16 conditional subtracts per 32 butterflies instead of Harvey's 32.
+#define ALOHA_GS_STAGE(NELEM, HALF, TWIDX)                                                          \
+    {                                                                                               \
+        Tw w_;                                                                                      \
+        _Pragma("unroll") for (int e = 0; e < (NELEM); ++e) {                                       \
+            if (e & (HALF)) continue;                                                               \
+            if ((e & ((HALF)-1)) == 0) {                                                            \
+                const int g0 = e & ~(2 * (HALF)-1);                                                 \
+                w_ = ldtw(tw + (TWIDX));                                                            \
+            }                                                                                       \
+            if (bnd[e] + bnd[e + (HALF)] > 16) {                                                    \
+                if (bnd[e] > 8) { x[e] = csub_s(x[e], q8); bnd[e] = 8; }                            \
+                if (bnd[e + (HALF)] > 8) { x[e + (HALF)] = csub_s(x[e + (HALF)], q8); bnd[e + (HALF)] = 8; } \
+            }                                                                                       \
+            const int by_ = bnd[e + (HALF)];                                                        \
+            const u64 off_ = by_ <= 2 ? q2 : by_ <= 4 ? q4 : q8;                                    \
+            const u64 d_ = x[e] - x[e + (HALF)] + off_;                                             \
+            x[e] = x[e] + x[e + (HALF)];                                                            \
+            x[e + (HALF)] = mul_shoup(d_, w_.w, w_.wp, nq);                                         \
+            bnd[e] += by_;                                                                          \
+            bnd[e + (HALF)] = 2;                                                                    \
+        }                                                                                           \
+    }
+// bring every register back under 2q
+#define ALOHA_GS_NORMALISE(NELEM)                                                                   \
+    _Pragma("unroll") for (int e = 0; e < (NELEM); ++e) {                                           \
+        if (bnd[e] > 8) x[e] = csub_s(x[e], q8);                                                    \
+        if (bnd[e] > 4) x[e] = csub_s(x[e], q4);                                                    \
+        if (bnd[e] > 2) x[e] = csub_s(x[e], q2);                                                    \
+        bnd[e] = 2;                                                                                 \
+    }
+// last stage of the whole transform: N^-1 folded in, both outputs multiplied, canonical results
+#define ALOHA_GS_LAST(NELEM)                                                                        \
+    _Pragma("unroll") for (int i = 0; i < (NELEM) / 2; ++i) {                                       \
+        if (bnd[i] + bnd[i + (NELEM) / 2] > 16) {                                                   \
+            if (bnd[i] > 8) { x[i] = csub_s(x[i], q8); bnd[i] = 8; }                                \
+            if (bnd[i + (NELEM) / 2] > 8) { x[i + (NELEM) / 2] = csub_s(x[i + (NELEM) / 2], q8); bnd[i + (NELEM) / 2] = 8; } \
+        }                                                                                           \
+        const int by_ = bnd[i + (NELEM) / 2];                                                       \
+        const u64 off_ = by_ <= 2 ? q2 : by_ <= 4 ? q4 : q8;                                        \
+        const u64 s_ = x[i] + x[i + (NELEM) / 2], d_ = x[i] - x[i + (NELEM) / 2] + off_;            \
+        x[i] = csub_s(mul_shoup(s_, job.mc.ninv, job.mc.ninv_p, nq), q);                            \
+        x[i + (NELEM) / 2] = csub_s(mul_shoup(d_, job.mc.wninv, job.mc.wninv_p, nq), q);            \
+    }
+
 template <int S1>
 __global__ void __launch_bounds__(256, ROWS_MINB) ntt_inv_rows(const NttJob *__restrict__ jobs, u32 total_rows) {
     constexpr int R = 1 << S1;
@@ -222,32 +265,26 @@ __global__ void __launch_bounds__(256, ROWS_MINB) ntt_inv_rows(const NttJob *__r
     if (grow >= total_rows) return;
     const NttJob &job = jobs[grow / R];
     const u32 r = grow % R;
-    const u64 q = job.mc.q, q2 = 2 * q, nq = 0 - q;
+    const u64 q = job.mc.q, q2 = 2 * q, q4 = 4 * q, q8 = 8 * q, nq = 0 - q;
     const u64 *src = job.src + (size_t)r * 256;
     u64 *dst = job.dst + (size_t)r * 256;
     const Tw *tw = job.tw;
     u64 *buf = smem + hw * kRowPad;
 
     u64 x[16];
+    int bnd[16];
 #pragma unroll
     for (int e = 0; e < 16; e += 2) {
         const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + 16 * h + e);
         x[e] = v.x;          // < 2q (see header)
         x[e + 1] = v.y;
+        bnd[e] = bnd[e + 1] = 2;
     }
     // lt = 0..3 pair e-bit lt
 #pragma unroll
-    for (int lt = 0; lt < 4; ++lt) {
-        const int half = 1 << lt;
-        const u32 base = (1u << (LOGN - 1 - lt)) + (r << (7 - lt));
-Tw w;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            if (e & half) continue;
-            if ((e & (half - 1)) == 0) w = ldtw(tw + base + ((16 * h + (e & ~(2 * half - 1))) >> (lt + 1)));
-            gs_bf(x[e], x[e + half], w, nq, q2);
-        }
-    }
+    for (int lt = 0; lt < 4; ++lt)
+        ALOHA_GS_STAGE(16, 1 << lt, (1u << (LOGN - 1 - lt)) + (r << (7 - lt)) + ((16 * h + g0) >> (lt + 1)))
+    ALOHA_GS_NORMALISE(16)
 #pragma unroll
     for (int e = 0; e < 16; e += 2) {
         ulonglong2 v;
@@ -261,26 +298,13 @@ Tw w;
     // lt = 4..7 pair k-bit (lt-4); idx = base + (k >> (lt - 3))
 #pragma unroll
     for (int lt = 4; lt < 8; ++lt) {
-        const int half = 1 << (lt - 4);
-        const u32 base = (1u << (LOGN - 1 - lt)) + (r << (7 - lt));
         if (S1 == 0 && lt == 7) {
-            // last stage of the whole transform: fold N^-1 in (both outputs multiplied)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const u64 s = x[i] + x[i + 8], d = x[i] - x[i + 8] + q2;
-                x[i] = csub_s(mul_shoup(s, job.mc.ninv, job.mc.ninv_p, nq), q);
-                x[i + 8] = csub_s(mul_shoup(d, job.mc.wninv, job.mc.wninv_p, nq), q);
-            }
+            ALOHA_GS_LAST(16)
         } else {
-Tw w;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                if (e & half) continue;
-                if ((e & (half - 1)) == 0) w = ldtw(tw + base + ((e & ~(2 * half - 1)) >> (lt - 3)));
-                gs_bf(x[e], x[e + half], w, nq, q2);
-            }
+            ALOHA_GS_STAGE(16, 1 << (lt - 4), (1u << (LOGN - 1 - lt)) + (r << (7 - lt)) + (g0 >> (lt - 3)))
         }
     }
+    if (S1 != 0) ALOHA_GS_NORMALISE(16)
 #pragma unroll
     for (int k = 0; k < 16; ++k) dst[h + 16 * k] = x[k];  // < 2q (canonical when S1 == 0)
 }
@@ -296,27 +320,23 @@ __global__ void __launch_bounds__(256, COLS_MINB) ntt_inv_cols(const NttJob *__r
     const NttJob &job = jobs[blockIdx.x / TILES];
     const int c0 = (blockIdx.x % TILES) * W;
     const int t = threadIdx.x, c = t % W, hg = t / W;
-    const u64 q = job.mc.q, q2 = 2 * q, nq = 0 - q;
+    const u64 q = job.mc.q, q2 = 2 * q, q4 = 4 * q, q8 = 8 * q, nq = 0 - q;
     const u64 *src = job.dst + c0 + c;   // the row pass has already moved the polynomial to job.dst
     u64 *dst = job.dst + c0 + c;
     const Tw *tw = job.tw;
 
     u64 x[E];
-    if (LB > 0) {
+    int bnd[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) bnd[e] = 2;
+    if constexpr (LB > 0) {
         // low LB stages on contiguous rows 16 G + e
 #pragma unroll
         for (int e = 0; e < E; ++e) x[e] = src[(size_t)(16 * hg + e) * 256];
 #pragma unroll
-        for (int b = 0; b < LB; ++b) {
-            const int half = 1 << b;
-Tw w;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                if (e & half) continue;
-                if ((e & (half - 1)) == 0) w = ldtw(tw + (1 << (S1 - 1 - b)) + ((16 * hg + (e & ~(2 * half - 1))) >> (b + 1)));
-                gs_bf(x[e], x[e + half], w, nq, q2);
-            }
-        }
+        for (int b = 0; b < LB; ++b)
+            ALOHA_GS_STAGE(E, 1 << b, (1 << (S1 - 1 - b)) + ((16 * hg + g0) >> (b + 1)))
+        ALOHA_GS_NORMALISE(E)
 #pragma unroll
         for (int e = 0; e < E; ++e) smem[(16 * hg + e) * W + c] = x[e];
         __syncthreads();
@@ -329,22 +349,10 @@ Tw w;
     // high LA stages on rows h + H k: b = LB .. S1-1 pairs k-bit (b - LB); idx = m + (k >> (b+1-LB))
 #pragma unroll
     for (int b = LB; b < S1; ++b) {
-        const int half = 1 << (b - LB);
         if (b == S1 - 1) {
-#pragma unroll
-            for (int i = 0; i < E / 2; ++i) {
-                const u64 s = x[i] + x[i + E / 2], d = x[i] - x[i + E / 2] + q2;
-                x[i] = csub_s(mul_shoup(s, job.mc.ninv, job.mc.ninv_p, nq), q);
-                x[i + E / 2] = csub_s(mul_shoup(d, job.mc.wninv, job.mc.wninv_p, nq), q);
-            }
+            ALOHA_GS_LAST(E)
         } else {
-Tw w;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                if (e & half) continue;
-                if ((e & (half - 1)) == 0) w = ldtw(tw + (1 << (S1 - 1 - b)) + ((e & ~(2 * half - 1)) >> (b + 1 - LB)));
-                gs_bf(x[e], x[e + half], w, nq, q2);
-            }
+            ALOHA_GS_STAGE(E, 1 << (b - LB), (1 << (S1 - 1 - b)) + (g0 >> (b + 1 - LB)))
         }
     }
 #pragma unroll
