@@ -269,6 +269,38 @@ struct Builder {
         return ALOHA_OK;
     }
 
+    // ALOHA_F_STRICT: the RTL's schedule, one op per stage, ping-ponging between the source register's
+    // buffer A and the destination's buffer B (ntt_fsm.sv:80).  With an odd number of stages the
+    // result lands in B and A keeps stage logN-2 (exactly the RTL); with an even number the
+    // RTL would leave them the other way round -- like the oracle, vd is defined to hold the result.
+    int strict_transform(const VecOp &proto, int src_reg, int wd, u64 n) {
+        const unsigned logn = ilog2(n);
+        Loc A;
+        int rc = alloc(&A, n);                 // private, writable copy of vs1's value
+        if (rc) return rc;
+        emit_copy(ptr(A), proto.a, n);
+        producer[A.off] = (int)ops.size() - 1;
+        Loc Bl;
+        rc = alloc(&Bl, n);
+        if (rc) return rc;
+        u64 *bufs[2] = {ptr(A), ptr(Bl)};
+        for (unsigned s = 0; s < logn; ++s) {
+            VecOp o = proto;
+            o.kind = proto.kind == K_NTT ? K_PEASE_F : K_PEASE_I;
+            o.alu = s;                          // stage number (also keeps stages in separate launches)
+            o.a = bufs[s & 1];
+            o.dst = bufs[(s + 1) & 1];
+            ops.push_back(o);
+        }
+        const bool result_in_B = logn & 1;
+        // the last stage wrote the result buffer, the one before it the other buffer
+        producer[(result_in_B ? Bl : A).off] = (int)ops.size() - 1;
+        producer[(result_in_B ? A : Bl).off] = (int)ops.size() - 2;
+        define(wd, result_in_B ? Bl : A);
+        define(src_reg, result_in_B ? A : Bl);
+        return ALOHA_OK;
+    }
+
     int step(const Inst &in, const aloha_vp_args &a, bool *brk) {
         ++instructions;
         const MicroOp m = expand(in, a.step);
@@ -343,14 +375,17 @@ struct Builder {
         if (m.ntt == 2 || m.ntt == 3) {
             src_reg = m.ntt == 2 ? rd(1) : rd(3);
             if (src_reg == wd) return fail(E, ALOHA_E_ILLEGAL, "VNTT/VINTT with vd == vs1");
-            if (mod_idx < 0) return fail(E, ALOHA_E_STATE, "VNTT/VINTT under a modulus with no twiddle ROM (aloha_load_tf_rom)");
+            int tf = mod_idx;
+            if (tf < 0 && (E->cfg.flags & ALOHA_F_STRICT) && !E->mod_q.empty())
+                tf = (int)E->mod_q.size() - 1;      // the RTL falls back to its last ROM (vxu_top.sv:115-116, Q6)
+            if (tf < 0) return fail(E, ALOHA_E_STATE, "VNTT/VINTT under a modulus with no twiddle ROM (aloha_load_tf_rom)");
             if (n > 65536) return fail(E, ALOHA_E_STATE, "VNTT/VINTT support N <= 65536");
             o.kind = m.ntt == 2 ? K_NTT : K_INTT;
-            o.mod = mod_idx;
+            o.mod = tf;
             int rc = read_loc(src_reg, n, &o.a);
             if (rc) return rc;
             const TwTable *t;
-            rc = get_tables(E, mod_idx, ilog2(n), &t);
+            rc = get_tables(E, tf, ilog2(n), &t);
             if (rc) return rc;
             ++limb_ntts;
         } else if (m.iconn == 1 || m.iconn == 2) {
@@ -381,6 +416,8 @@ struct Builder {
             }
             o.s = m.scalar_alu >= q ? m.scalar_alu - q : m.scalar_alu;   // modalu.sv:46
         }
+        if ((o.kind == K_NTT || o.kind == K_INTT) && (E->cfg.flags & ALOHA_F_STRICT))
+            return strict_transform(o, src_reg, wd, n);
         Loc nl;
         int rc = alloc(&nl, n);
         if (rc) return rc;
@@ -644,6 +681,14 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
                 switch (o.kind) {
                 case K_EW: append(tables, EwJob{o.dst, o.a, o.b, o.s, o.q, o.iq}); break;
                 case K_COPY: append(tables, CopyJob{o.dst, o.a}); break;
+                case K_PEASE_F:
+                case K_PEASE_I: {
+                    const TwTable *tw;
+                    int rc = get_tables(E, o.mod, ilog2(o.n), &tw);
+                    if (rc) return rc;
+                    append(tables, PeaseJob{o.dst, o.a, o.kind == K_PEASE_F ? tw->fwd : tw->inv, o.q, o.iq});
+                    break;
+                }
                 case K_MULADD: append(tables, MulAddJob{o.dst, o.c, o.a, o.b, o.q, o.iq}); break;
                 case K_SOP: {
                     const size_t at = append(tables, SopJob{o.dst, nullptr, o.q, o.iq, (u32)o.terms.size(), 0});
@@ -709,6 +754,8 @@ int issue(aloha *E, const Plan &plan, u64 *launched) {
         switch (L.kind) {
         case K_EW: e = launch_ew(L.alu, (const EwJob *)tab, L.njobs, L.n, E->stream); break;
         case K_COPY: e = launch_copy((const CopyJob *)tab, L.njobs, L.n, E->stream); break;
+        case K_PEASE_F: e = launch_pease((const PeaseJob *)tab, L.njobs, ilog2(L.n), L.alu, false, E->stream); break;
+        case K_PEASE_I: e = launch_pease((const PeaseJob *)tab, L.njobs, ilog2(L.n), L.alu, true, E->stream); break;
         case K_MULADD: e = launch_muladd((const MulAddJob *)tab, L.njobs, L.n, E->stream); break;
         case K_SOP: e = launch_sop((const SopJob *)tab, L.njobs, L.n, E->stream); break;
         case K_AUTMAC: e = launch_autmac((const AutMacJob *)tab, L.njobs, L.n, E->stream); break;

@@ -40,7 +40,7 @@ struct Loc {
     u64 n = 0;     // valid words
 };
 
-enum OpKind : uint8_t { K_EW = 0, K_NTT, K_INTT, K_VAUT, K_VROLI, K_COPY, K_MULADD, K_AUTMAC, K_SOP };
+enum OpKind : uint8_t { K_EW = 0, K_NTT, K_INTT, K_VAUT, K_VROLI, K_COPY, K_MULADD, K_AUTMAC, K_SOP, K_PEASE_F, K_PEASE_I };
 
 struct VecOp {
     OpKind kind;

@@ -52,6 +52,16 @@ struct PermJob {
     u64 kinv;              // VAUT: k^-1 mod n (gather form); VROLI: rot mod n
 };
 
+// One stage of the reference's constant-geometry schedule, word-exact (ALOHA_F_STRICT):
+//   forward  : dst[2p] = add(r(x[p]), m), dst[2p+1] = sub(r(x[p]), m), m = barrett(r(x[p+N/2]), w), w = tw[2^s + (p mod 2^s)]
+//   inverse  : dst[p] = half(add(x[2p], x[2p+1])), dst[p+N/2] = half(barrett(sub(x[2p], x[2p+1]), w)), w = itw[2^f + (p mod 2^f)], f = logN-1-s
+struct PeaseJob {
+    u64 *dst;
+    const u64 *src;
+    const Tw *tw;
+    u64 q, iq;
+};
+
 struct CopyJob {
     u64 *dst;
     const u64 *src;
@@ -96,6 +106,7 @@ cudaError_t launch_ntt_inverse(const NttJob *jobs_dev, u32 njobs, u32 logn, cuda
 cudaError_t launch_ew(u32 alu_op, const EwJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
 cudaError_t launch_vaut(const PermJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
 cudaError_t launch_vroli(const PermJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
+cudaError_t launch_pease(const PeaseJob *jobs_dev, u32 njobs, u32 logn, u32 stage, bool inverse, cudaStream_t st);
 cudaError_t launch_copy(const CopyJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
 cudaError_t launch_mac(const MacJob *jobs_dev, u32 njobs, u32 terms, u32 n, cudaStream_t st);
 cudaError_t launch_autmac(const AutMacJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);

@@ -16,7 +16,7 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
-FLAG_SETS = [0, A.F_NO_BATCH, A.F_NO_ALIAS, A.F_NO_BATCH | A.F_NO_ALIAS, A.F_GRAPHS, A.F_NO_FUSE]
+FLAG_SETS = [0, A.F_NO_BATCH, A.F_NO_ALIAS, A.F_NO_BATCH | A.F_NO_ALIAS, A.F_GRAPHS, A.F_NO_FUSE, A.F_STRICT]
 
 
 def tv_engine(flags=0):
@@ -448,3 +448,34 @@ def test_edge_cases_empty_batch_mixed_vl_and_last_rows():
     assert e.value.name == "E_RANGE"
     with pytest.raises(A.AlohaError):
         eng.dma_mem_h2d(rows - 1, np.zeros(256, dtype=np.uint64))
+
+
+@pytest.mark.parametrize("n", [1024, 8192])
+def test_strict_mode_matches_rtl_on_garbage_inputs_and_clobbered_source(n):
+    """ALOHA_F_STRICT: raw 64-bit input words (far above 2q), the ping-pong intermediate the RTL leaves
+    in the source register, and the ROM fallback for an unknown modulus (Q6) -- all three
+    are outside the fast path's contract and must equal the oracle word for word here."""
+    rp = n // 128
+    q, psi = O.Q0, pow(O.PSI0, 8192 // n, O.Q0)
+    odd_q = O.Q1                                   # no ROM provisioned for it: falls back to the last table
+    rng = np.random.default_rng(n)
+    raw = rng.integers(0, 2**64, n, dtype=np.uint64)
+    prog = asm.Program().vsetvl(n).vsetq(q).vle(0, 0, 0).vntt(2, 0).vse(2, 2, 0).vse(0, 2, rp)   # result, clobbered source
+    prog.vle(4, 0, 0).vintt(6, 4).vse(6, 2, 2 * rp).vse(4, 2, 3 * rp)
+    prog.vsetq(odd_q).vle(1, 0, 0).vntt(3, 1).vse(3, 2, 4 * rp).brk()
+    machines = [A.Engine(vlmax_bits=n * 64, spm_rows=8 * rp, ksk_rows=0, moduli=[(q, psi)], flags=A.F_STRICT),
+                O.GoldenModel(vlmax_bits=n * 64, spm_rows=8 * rp, ksk_rows=0, moduli=[(q, psi)])]
+    outs = []
+    for m in machines:
+        m.load_isram(prog.words(), 0)
+        m.dma_mem_h2d(0, raw)
+        m.run_vp(0, 0, 0, rp)
+        outs.append(m.dma_mem_d2h(rp, 5 * n))
+    assert (outs[0] == outs[1]).all(), [int((outs[0][i * n:(i + 1) * n] != outs[1][i * n:(i + 1) * n]).sum()) for i in range(5)]
+    # the fast path refuses the same stream instead of guessing
+    eng = A.Engine(vlmax_bits=n * 64, spm_rows=8 * rp, ksk_rows=0, moduli=[(q, psi)])
+    eng.load_isram(prog.words(), 0)
+    eng.dma_mem_h2d(0, raw)
+    with pytest.raises(A.AlohaError) as e:
+        eng.run_vp(0, 0, 0, rp)
+    assert e.value.name == "E_UNDEFINED"
