@@ -47,6 +47,8 @@ def main(argv=None) -> int:
     ap.add_argument("--ksk", nargs="*", default=[], metavar="STEP:FILE")
     ap.add_argument("--cipher", nargs="*", default=[], metavar="DRAMADDR:FILE")
     ap.add_argument("--encoder", nargs="*", default=[], metavar="OP:FILE")
+    ap.add_argument("--dram-image", help="$readmemh image of the whole DDR (512-bit words, top_noaxilite_tb.sv:339-346); "
+                    "rotation keys are then DMA'd from it as the testbench's load_ksk does")
     ap.add_argument("--dump-dir", required=True)
     ap.add_argument("--expect", help="expected final result (case3_expected_result.txt format)")
     ap.add_argument("-n", type=int, default=8192)
@@ -63,6 +65,13 @@ def main(argv=None) -> int:
         step, path = item.split(":", 1)
         eng.dma_ksk_h2d((clog2(int(step)) - 1) * a.n * 12 // 128, read_poly_text(path))
     host = HostDriver(eng, open(a.program).read(), a.n)
+    if a.dram_image:
+        from . import dram_image as D
+        img = D.read_readmemh(a.dram_image, total_words=(64 << 20) // 64)
+        host.dram_write(0, img)
+        if not a.ksk:      # load_ksk(KSK_DRAM_BASE): 3 keys x 12 N u64 in one DMA (tb:372-394, 715)
+            n_ksk = 3 * 12 * a.n
+            eng.dma_ksk_h2d(0, img[D.KSK_DRAM_BASE // 8:D.KSK_DRAM_BASE // 8 + n_ksk])
     for item in a.cipher:
         addr, path = item.split(":", 1)
         host.dram_write(DRAM_VP_BASE + int(addr, 0), read_poly_text(path))

@@ -92,3 +92,26 @@ def test_dump_text_format(tmp_path):
     path = str(tmp_path / "inst_0_out.txt")
     A.HostDriver.write_dump_text(path, data, wr)
     assert open(path).read() == "5\nx\n9223372036854775809\n7\n"
+
+
+def test_readmemh_dram_image_roundtrip(tmp_path):
+    """512-bit-per-line $readmemh images (top_noaxilite_tb.sv:339-346): u64 number 0 of a DDR word is the
+    LAST 16 hex digits of its line; @address records, x digits and comments are honoured."""
+    from aloha_b200 import dram_image as D
+    rng = np.random.default_rng(0)
+    data = rng.integers(0, 2**64, 64, dtype=np.uint64)
+    path = str(tmp_path / "img.mem")
+    D.write_readmemh(path, data)
+    first = open(path).readline().strip()
+    assert len(first) == 128 and int(first[-16:], 16) == int(data[0]) and int(first[:16], 16) == int(data[7])
+    assert (D.read_readmemh(path) == data).all()
+    with open(path, "a") as f:
+        f.write("// a sparse record\n@10\n" + "0" * 112 + "00000000_0000xx2a\n")
+    back = D.read_readmemh(path, total_words=20)
+    assert (back[:64] == data).all() and back[16 * 8] == 0x2a and not back[64:16 * 8].any()
+    ct = rng.integers(0, 2**60, 4 * 8192, dtype=np.uint64)
+    ksk = rng.integers(0, 2**60, 12 * 8192, dtype=np.uint64)
+    img = D.build_image(64 << 20, ciphertexts={0: ct}, ksks={8: ksk})
+    assert (img[D.DRAM_VP_BASE // 8:D.DRAM_VP_BASE // 8 + len(ct)] == ct).all()
+    base = (D.KSK_DRAM_BASE + 2 * D.KSK_SLOT_BYTES) // 8              # step 8 -> third slot
+    assert (img[base:base + len(ksk)] == ksk).all() and D.KSK_SLOT_BYTES == 786432

@@ -479,3 +479,46 @@ def test_strict_mode_matches_rtl_on_garbage_inputs_and_clobbered_source(n):
     with pytest.raises(A.AlohaError) as e:
         eng.run_vp(0, 0, 0, rp)
     assert e.value.name == "E_UNDEFINED"
+
+
+def test_replay_cli_from_readmemh_dram_image(tmp_path):
+    """case0_4_4 again, this time from a single $readmemh DDR image (ciphertext at DRAM_VP_BASE, the
+    rotation key in its KSK slot) as the reference's DRAM_INPUT_FILE would provide it."""
+    from aloha_b200 import dram_image as D, replay
+    m = G.manifest()
+    n, entry = m["n"], m["cases"]["case0_4_4"]
+    ops, dram, enc, ksk = G.case_inputs("case0_4_4")
+    img = D.build_image(64 << 20, ciphertexts={ops[int(i)].dram_addr: G.pool(k) for i, k in entry["loads"].items()},
+                        ksks={2: ksk[0]})
+    D.write_readmemh(str(tmp_path / "dram.mem"), img[:(D.DRAM_VP_BASE + 4 * n * 8) // 8])
+    (tmp_path / "prog.txt").write_text("\n".join(entry["program"]) + "\n")
+    args = ["--program", str(tmp_path / "prog.txt"), "--isram", G.write_microcode_dir(str(tmp_path / "isram")),
+            "--dram-image", str(tmp_path / "dram.mem"), "--dump-dir", str(tmp_path / "out"), "--encoder"]
+    for i, data in enc.items():
+        with open(tmp_path / f"enc{i}.txt", "w") as f:
+            f.write("\n".join(str(int(v)) for v in data) + "\n")
+        args.append(f"{i}:{tmp_path / f'enc{i}.txt'}")
+    assert replay.main(args) == 0
+    toks = (tmp_path / "out" / "inst_7_out.txt").read_text().split()
+    data = np.array([int(t) for t in toks], dtype=np.uint64)
+    assert G.poly_hashes(data, np.ones(len(data), bool), n) == entry["dumps"]["inst_7_out"]
+
+
+def test_vfqsub_sv_follows_the_rtl_operand():
+    """VFQSUB.sv computes imm - vs2 with the vector operand taken from vs2 (expander.v:342-363), not vs1 as
+    the reference's own decode golden expects -- GPU, oracle and exact arithmetic agree."""
+    n, q = 256, O.Q0
+    imm = 0x123456789
+    eng = A.Engine(vlmax_bits=n * 64, spm_rows=8, ksk_rows=0, moduli=())
+    p = asm.Program().vsetvl(n).vsetq(q).vle(4, 0, 0).vle(7, 0, 2).vfqsub_sv(2, imm, 4).vse(2, 2, 0).brk()
+    rng = np.random.default_rng(1)
+    a, b = rng.integers(0, q, n, dtype=np.uint64), rng.integers(0, q, n, dtype=np.uint64)
+    gm = O.GoldenModel(vlmax_bits=n * 64, spm_rows=8, ksk_rows=0, moduli=())
+    outs = []
+    for mach in (eng, gm):
+        mach.load_isram(p.words(), 0)
+        mach.dma_mem_h2d(0, np.concatenate([a, b]))
+        mach.run_vp(0, 0, 0, 4)
+        outs.append(mach.dma_mem_d2h(4, n))
+    want = np.array([(imm - int(v)) % q for v in a], dtype=np.uint64)
+    assert (outs[0] == want).all() and (outs[1] == want).all()
