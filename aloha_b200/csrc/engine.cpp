@@ -913,6 +913,39 @@ int run_batch(aloha *E, const uint32_t *pcs, bool same_pc, uint32_t count, const
     return ALOHA_OK;
 }
 
+// ALOHA_F_DEFER: plan and launch everything queued so far as one batch.
+int flush_queue(aloha *E) {
+    if (E->queued_pcs.empty()) return ALOHA_OK;
+    std::vector<uint32_t> pcs;
+    std::vector<aloha_vp_args> args;
+    pcs.swap(E->queued_pcs);
+    args.swap(E->queued_args);
+    int rc = run_batch(E, pcs.data(), false, (uint32_t)pcs.size(), args.data());
+    if (rc == ALOHA_OK || rc == ALOHA_E_CUDA) return rc;
+    // A queued call is malformed.  Planning fails before anything is launched, so replay the queue call
+    // by call: everything before the offender takes effect, exactly as without ALOHA_F_DEFER.
+    for (size_t c = 0; c < pcs.size(); ++c) {
+        rc = run_batch(E, &pcs[c], true, 1, &args[c]);
+        if (rc) return rc;
+    }
+    return ALOHA_OK;
+}
+#define FLUSH()                          \
+    do {                                 \
+        int frc_ = flush_queue(E);       \
+        if (frc_) return frc_;           \
+    } while (0)
+
+int enqueue_or_run(aloha *E, const uint32_t *pcs, bool same_pc, uint32_t count, const aloha_vp_args *args) {
+    if (!(E->cfg.flags & ALOHA_F_DEFER)) return run_batch(E, pcs, same_pc, count, args);
+    for (uint32_t c = 0; c < count; ++c) {
+        E->queued_pcs.push_back(same_pc ? pcs[0] : pcs[c]);
+        E->queued_args.push_back(args[c]);
+    }
+    if (E->queued_pcs.size() >= 4096) return flush_queue(E);   // bound the plan size
+    return ALOHA_OK;
+}
+
 // A host-side write into SPM words [off, off+n): registers aliasing the range move out first.
 int cow_for_host_write(aloha *E, u64 off, u64 n) {
     bool any = false;
@@ -1015,6 +1048,7 @@ void aloha_destroy(aloha_t *E) {
 
 int aloha_load_isram(aloha_t *E, const uint8_t *words, uint32_t n, uint32_t at_pc) {
     if (!E || !words) return ALOHA_E_ARG;
+    FLUSH();
     if ((u64)at_pc + n > E->iram_depth) return fail(E, ALOHA_E_RANGE, "beyond the instruction ROM (cfg.isram_depth)");
     std::memcpy(&E->isram[(size_t)at_pc * 12], words, (size_t)n * 12);
     ++E->isram_version;
@@ -1023,6 +1057,7 @@ int aloha_load_isram(aloha_t *E, const uint8_t *words, uint32_t n, uint32_t at_p
 
 int aloha_load_tf_rom(aloha_t *E, const uint64_t *q, const uint64_t *psi, uint32_t n) {
     if (!E || !q || !psi) return ALOHA_E_ARG;
+    FLUSH();
     CU(cudaStreamSynchronize(E->stream));
     free_tables(E);
     E->mod_q.assign(q, q + n);
@@ -1036,6 +1071,7 @@ int aloha_load_tf_rom(aloha_t *E, const uint64_t *q, const uint64_t *psi, uint32
 
 int aloha_dma_mem_h2d(aloha_t *E, uint32_t row, const uint64_t *src, uint64_t bytes) {
     if (!E || !src || bytes % 64) return ALOHA_E_ARG;
+    FLUSH();
     const u64 off = (u64)row * kLanes, n = bytes / 8;
     if (off + n > E->spm_words) return fail(E, ALOHA_E_RANGE, "DMA beyond SPM");
     int rc = cow_for_host_write(E, off, n);
@@ -1048,6 +1084,7 @@ int aloha_dma_mem_h2d(aloha_t *E, uint32_t row, const uint64_t *src, uint64_t by
 
 int aloha_dma_mem_h2d_async(aloha_t *E, uint32_t row, const uint64_t *src, uint64_t bytes) {
     if (!E || !src || bytes % 64) return ALOHA_E_ARG;
+    FLUSH();
     const u64 off = (u64)row * kLanes, n = bytes / 8;
     if (off + n > E->spm_words) return fail(E, ALOHA_E_RANGE, "DMA beyond SPM");
     int rc = cow_for_host_write(E, off, n);
@@ -1077,6 +1114,7 @@ int aloha_dma_mem_h2d_async(aloha_t *E, uint32_t row, const uint64_t *src, uint6
 
 int aloha_dma_mem_d2h_async(aloha_t *E, uint64_t *dst, uint32_t row, uint64_t bytes) {
     if (!E || !dst || bytes % 64) return ALOHA_E_ARG;
+    FLUSH();
     const u64 off = (u64)row * kLanes, n = bytes / 8;
     if (off + n > E->spm_words) return fail(E, ALOHA_E_RANGE, "DMA beyond SPM");
     if (!E->up_stream) {
@@ -1100,6 +1138,7 @@ int aloha_dma_mem_d2h_async(aloha_t *E, uint64_t *dst, uint32_t row, uint64_t by
 
 int aloha_dma_mem_d2h(aloha_t *E, uint64_t *dst, uint32_t row, uint64_t bytes) {
     if (!E || !dst || bytes % 64) return ALOHA_E_ARG;
+    FLUSH();
     const u64 off = (u64)row * kLanes, n = bytes / 8;
     if (off + n > E->spm_words) return fail(E, ALOHA_E_RANGE, "DMA beyond SPM");
     CU(cudaMemcpyAsync(dst, E->d_spm + off, bytes, cudaMemcpyDeviceToHost, E->stream));
@@ -1109,6 +1148,7 @@ int aloha_dma_mem_d2h(aloha_t *E, uint64_t *dst, uint32_t row, uint64_t bytes) {
 
 int aloha_dma_ksk_h2d(aloha_t *E, uint32_t row, const uint64_t *src, uint64_t bytes) {
     if (!E || !src || bytes % 64) return ALOHA_E_ARG;
+    FLUSH();
     const u64 off = (u64)row * kLanes, n = bytes / 8;
     if (off + n > E->ksk_words) return fail(E, ALOHA_E_RANGE, "DMA beyond KSK memory");
     // registers aliasing KSK rows (VLE base 15) keep the OLD key: move them out first
@@ -1132,6 +1172,7 @@ int aloha_dma_ksk_h2d(aloha_t *E, uint32_t row, const uint64_t *src, uint64_t by
 
 int aloha_spm_written(aloha_t *E, uint32_t row, uint64_t nwords, uint8_t *out) {
     if (!E || !out) return ALOHA_E_ARG;
+    FLUSH();
     const u64 off = (u64)row * kLanes;
     if (off + nwords > E->spm_words) return fail(E, ALOHA_E_RANGE, "range beyond SPM");
     for (u64 i = 0; i < nwords; ++i) out[i] = E->written[(off + i) / 8];
@@ -1142,21 +1183,22 @@ int aloha_run_vp(aloha_t *E, uint32_t pc, uint32_t src0, uint32_t src1, uint32_t
                  uint32_t step) {
     if (!E) return ALOHA_E_ARG;
     const aloha_vp_args a{src0, src1, rslt, ksk_ptr, step};
-    return run_batch(E, &pc, true, 1, &a);
+    return enqueue_or_run(E, &pc, true, 1, &a);
 }
 
 int aloha_run_vp_batch(aloha_t *E, uint32_t pc, uint32_t count, const aloha_vp_args *args) {
     if (!E || (count && !args)) return ALOHA_E_ARG;
-    return run_batch(E, &pc, true, count, args);
+    return enqueue_or_run(E, &pc, true, count, args);
 }
 
 int aloha_run_vp_multi(aloha_t *E, uint32_t count, const uint32_t *pcs, const aloha_vp_args *args) {
     if (!E || (count && (!args || !pcs))) return ALOHA_E_ARG;
-    return run_batch(E, pcs, false, count, args);
+    return enqueue_or_run(E, pcs, false, count, args);
 }
 
 int aloha_sync(aloha_t *E) {
     if (!E) return ALOHA_E_ARG;
+    FLUSH();
     CU(cudaStreamSynchronize(E->stream));
     if (E->up_stream) {
         CU(cudaStreamSynchronize(E->up_stream));
@@ -1169,18 +1211,21 @@ int aloha_sync(aloha_t *E) {
 
 int aloha_spm_device_ptr(aloha_t *E, uint32_t row, void **p) {
     if (!E || !p) return ALOHA_E_ARG;
+    FLUSH();
     if (row >= E->cfg.spm_rows) return fail(E, ALOHA_E_RANGE, "row beyond SPM");
     *p = E->d_spm + (u64)row * kLanes;
     return ALOHA_OK;
 }
 int aloha_ksk_device_ptr(aloha_t *E, uint32_t row, void **p) {
     if (!E || !p) return ALOHA_E_ARG;
+    FLUSH();
     if (row >= E->cfg.ksk_rows) return fail(E, ALOHA_E_RANGE, "row beyond KSK memory");
     *p = E->d_ksk + (u64)row * kLanes;
     return ALOHA_OK;
 }
 int aloha_spm_mark_written(aloha_t *E, uint32_t row, uint32_t nrows) {
     if (!E) return ALOHA_E_ARG;
+    FLUSH();
     if ((u64)row + nrows > E->cfg.spm_rows) return fail(E, ALOHA_E_RANGE, "rows beyond SPM");
     int rc = cow_for_host_write(E, (u64)row * kLanes, (u64)nrows * kLanes);
     if (rc) return rc;
@@ -1189,18 +1234,23 @@ int aloha_spm_mark_written(aloha_t *E, uint32_t row, uint32_t nrows) {
 }
 int aloha_set_stream(aloha_t *E, void *stream) {
     if (!E) return ALOHA_E_ARG;
+    FLUSH();
     CU(cudaStreamSynchronize(E->stream));
     E->stream = stream ? (cudaStream_t)stream : E->own_stream;
     return ALOHA_OK;
 }
 
-int aloha_get_stats(const aloha_t *E, aloha_stats *out) {
-    if (!E || !out) return ALOHA_E_ARG;
+int aloha_get_stats(const aloha_t *Ec, aloha_stats *out) {
+    if (!Ec || !out) return ALOHA_E_ARG;
+    aloha_t *E = const_cast<aloha_t *>(Ec);   // logically const: queued calls are part of the observable state
+    FLUSH();
     *out = E->stats;
     return ALOHA_OK;
 }
-int aloha_get_csr(const aloha_t *E, uint64_t *vl, uint64_t *q, uint64_t *iq) {
-    if (!E) return ALOHA_E_ARG;
+int aloha_get_csr(const aloha_t *Ec, uint64_t *vl, uint64_t *q, uint64_t *iq) {
+    if (!Ec) return ALOHA_E_ARG;
+    aloha_t *E = const_cast<aloha_t *>(Ec);
+    FLUSH();
     if (vl) *vl = E->vl;
     if (q) *q = E->q;
     if (iq) *iq = E->iq;

@@ -443,6 +443,7 @@ def measure_tv_latency(A):
         first, steady, st = gpu_once()
         _, steady_nodump, _ = gpu_once(dumps=False)
         _, steady_graphs, _ = gpu_once(flags=A.F_GRAPHS, dumps=False)
+        _, steady_defer, st_defer = gpu_once(flags=A.F_DEFER | A.F_GRAPHS, dumps=False)
         model = O.GoldenModel()
         for words, pc in G.microcode():
             model.load_isram(words, pc)
@@ -454,6 +455,8 @@ def measure_tv_latency(A):
         cpu = time.perf_counter() - t0
         out[case] = {"ops": len(ops), "gpu_ms_first_run": 1e3 * first, "gpu_ms_steady": 1e3 * steady,
                      "gpu_ms_steady_no_dumps": 1e3 * steady_nodump, "gpu_ms_steady_no_dumps_cuda_graphs": 1e3 * steady_graphs,
+                     "gpu_ms_steady_no_dumps_deferred_queue_cuda_graphs": 1e3 * steady_defer,
+                     "kernel_launches_deferred_queue": st_defer["kernel_launches"],
                      "cpu_oracle_ms_1thread": 1e3 * cpu, "kernel_launches": st["kernel_launches"],
                      "note": "gpu_ms_steady includes every per-op DMA and the 256 KiB dump read-back the testbench does after each op; the no_dumps figures run the same ops with one sync at the end"}
     return out

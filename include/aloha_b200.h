@@ -64,6 +64,11 @@ enum {
     ALOHA_F_NO_ALIAS = 1u << 1,  /* materialise every VLE / VSE as a copy (debug) */
     ALOHA_F_GRAPHS = 1u << 2,    /* replay cached plans as CUDA graphs */
     ALOHA_F_NO_FUSE = 1u << 3,   /* keep VAUT / VFQMUL / VFQADD chains as separate kernels */
+    ALOHA_F_DEFER = 1u << 5,     /* PROGRAM-level scheduling: aloha_run_vp* only queue the call; the queue is planned and
+                                    launched as ONE batch at the next DMA / aloha_sync / state query, so consecutive host
+                                    ops (mul_plain, hom_add, rotate ... of one program) share launches wherever their
+                                    data dependencies allow.  Results are identical; an error in a queued call is
+                                    reported by the call that flushes it. */
     ALOHA_F_STRICT = 1u << 4     /* VNTT / VINTT run the RTL's constant-geometry schedule stage by stage with the
                                     RTL ALU: word-exact for ANY input (also >= 2q) and the source register keeps the
                                     ping-pong intermediate the RTL leaves there.  ~10x slower transforms. */

@@ -16,7 +16,7 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
-FLAG_SETS = [0, A.F_NO_BATCH, A.F_NO_ALIAS, A.F_NO_BATCH | A.F_NO_ALIAS, A.F_GRAPHS, A.F_NO_FUSE, A.F_STRICT]
+FLAG_SETS = [0, A.F_NO_BATCH, A.F_NO_ALIAS, A.F_NO_BATCH | A.F_NO_ALIAS, A.F_GRAPHS, A.F_NO_FUSE, A.F_STRICT, A.F_DEFER]
 
 
 def tv_engine(flags=0):
@@ -522,3 +522,36 @@ def test_vfqsub_sv_follows_the_rtl_operand():
         outs.append(mach.dma_mem_d2h(4, n))
     want = np.array([(imm - int(v)) % q for v in a], dtype=np.uint64)
     assert (outs[0] == want).all() and (outs[1] == want).all()
+
+
+def test_deferred_queue_batches_across_calls_and_keeps_error_semantics():
+    """ALOHA_F_DEFER: sixteen separate run_vp calls become one plan (two launches) at the next DMA; a
+    malformed call in the queue still lets the calls before it take effect."""
+    n, L, B = 4096, 2, 8
+    rp = n // 128
+    primes, psis = synth(n, L)
+    per_poly = L * rp
+    rng = np.random.default_rng(12)
+    x = np.stack([rng.integers(0, primes[i % L], n, dtype=np.uint64) for i in range(B * L)])
+    want = O.NttTables(n, primes, psis).batch(x.copy(), np.arange(B * L) % L)
+    eng = A.Engine(vlmax_bits=n * 64, spm_rows=2 * B * per_poly, ksk_rows=0, moduli=list(zip(primes, psis)), flags=A.F_DEFER)
+    eng.load_isram(asm.transform_stream(n, primes).words(), 0)
+    eng.load_isram(asm.Program().vsetvl(n).vle(0, 0, 60000).brk().words(), 512)     # E_RANGE when it runs
+    eng.dma_mem_h2d(0, x.reshape(-1))
+    for b in range(B):
+        eng.run_vp(0, b * per_poly, 0, (B + b) * per_poly)                           # queued, not launched
+    got = eng.dma_mem_d2h(B * per_poly, B * L * n).reshape(B * L, n)                 # flush point
+    assert (got == want).all()
+    st = eng.stats()
+    assert st["kernel_launches"] == 2 and st["plans_built"] == 1
+    # error semantics
+    eng.dma_mem_h2d(B * per_poly, np.zeros(B * L * n, dtype=np.uint64))
+    eng.run_vp(0, 0, 0, B * per_poly)            # fine
+    eng.run_vp(512)                              # malformed; not noticed yet
+    eng.run_vp(0, per_poly, 0, (B + 1) * per_poly)
+    with pytest.raises(A.AlohaError) as e:
+        eng.sync()
+    assert e.value.name == "E_RANGE"
+    out = eng.dma_mem_d2h(B * per_poly, 2 * L * n).reshape(2 * L, n)
+    assert (out[:L] == want[:L]).all()           # the call before the offender ran
+    assert not out[L:].any()                     # the one after it did not
