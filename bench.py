@@ -212,7 +212,9 @@ def run_gpu(args):
         else:
             out = measure_rotmac(torch, A, asm, {"device": local}, primes, psis, stream, timed0, 16)
         if rank == 0:
-            print(json.dumps(out))
+            print(json.dumps(out), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
         return
     eng = A.Engine(vlmax_bits=N * 64, spm_rows=2 * rows, ksk_rows=0, device=local, moduli=list(zip(primes, psis)),
                    l2_chunk_bytes=args.chunk_mib << 20)
