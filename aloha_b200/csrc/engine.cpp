@@ -43,10 +43,16 @@ u64 bitrev(u64 x, unsigned bits) {
     for (unsigned i = 0; i < bits; ++i) { r = (r << 1) | (x & 1); x >>= 1; }
     return r;
 }
-Tw shoup(u64 w, u64 q) {
+// q = 2^60 - d with d <= 2^27: the transforms use the split-product arithmetic (modarith.cuh mul_pm)
+u32 modulus_form(const aloha *E, u64 q) {
+    if (E->cfg.flags & ALOHA_F_GENERIC_MODMUL) return FORM_GENERIC;
+    return (q < (1ull << 60) && (1ull << 60) - q <= (1ull << 27)) ? FORM_PM : FORM_GENERIC;
+}
+// twiddle pair in the form's layout (kernels.cuh Tw)
+Tw twiddle(u64 w, u64 q, u32 form) {
     Tw t;
     t.w = w;
-    t.wp = (u64)(((u128)w << 64) / q);
+    t.wp = form == FORM_PM ? (u64)(((u128)w << 32) % q) : (u64)(((u128)w << 64) / q);
     return t;
 }
 
@@ -64,33 +70,45 @@ int get_tables(aloha *E, int mod, unsigned logn, const TwTable **out) {
     const u64 psi = powmod(E->mod_psi[mod], E->nmax / n, q);
     if (powmod(psi, n, q) != q - 1) return fail(E, ALOHA_E_STATE, "psi is not a primitive 2N-th root of unity");
     const u64 ipsi = powmod(psi, q - 2, q);
+    const u32 form = modulus_form(E, q);
     std::vector<Tw> fwd(n), inv(n);
     u64 cf = 1, ci = 1;
     for (u64 e = 0; e < n; ++e) {
         const u64 j = bitrev(e, logn);
-        fwd[j] = shoup(cf, q);
-        inv[j] = shoup(ci, q);
+        fwd[j] = twiddle(cf, q, form);
+        inv[j] = twiddle(ci, q, form);
         cf = (u64)((u128)cf * psi % q);
         ci = (u64)((u128)ci * ipsi % q);
     }
+    // the forward row pass's view: row r of the N/256 x 256 layout uses tw[((R + r) << u) + j], u < 8
+    const u64 R = n / 256;
+    std::vector<Tw> fwd_rows(n, Tw{0, 0});
+    for (u64 r = 0; r < R; ++r)
+        for (u32 u = 0; u < 8; ++u)
+            for (u32 j = 0; j < (1u << u); ++j) fwd_rows[r * 256 + row_slot(u, j)] = fwd[((R + r) << u) + j];
     TwTable t;
     CU(cudaMalloc(&t.fwd, n * sizeof(Tw)));
     CU(cudaMalloc(&t.inv, n * sizeof(Tw)));
+    CU(cudaMalloc(&t.fwd_rows, n * sizeof(Tw)));
     CU(cudaMemcpy(t.fwd, fwd.data(), n * sizeof(Tw), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(t.inv, inv.data(), n * sizeof(Tw), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t.fwd_rows, fwd_rows.data(), n * sizeof(Tw), cudaMemcpyHostToDevice));
     const u64 ninv = powmod(n % q, q - 2, q);
-    const Tw a = shoup(ninv, q), b = shoup((u64)((u128)inv[1].w * ninv % q), q);
+    const Tw a = twiddle(ninv, q, form), b = twiddle((u64)((u128)inv[1].w * ninv % q), q, form);
     t.mc.q = q;
     t.mc.ninv = a.w; t.mc.ninv_p = a.wp;
     t.mc.wninv = b.w; t.mc.wninv_p = b.wp;
     t.mc.mest = (u32)((((u128)1) << 91) / q);
     t.mc.pre = 0;
+    t.mc.form = form;
+    t.mc.d = form == FORM_PM ? (u32)((1ull << 60) - q) : 0;
+    t.mc.q3 = 3 * q;
     *out = &(E->tw_tables[key] = t);
     return ALOHA_OK;
 }
 
 void free_tables(aloha *E) {
-    for (auto &kv : E->tw_tables) { cudaFree(kv.second.fwd); cudaFree(kv.second.inv); }
+    for (auto &kv : E->tw_tables) { cudaFree(kv.second.fwd); cudaFree(kv.second.inv); cudaFree(kv.second.fwd_rows); }
     E->tw_tables.clear();
 }
 void free_plans(aloha *E) {
@@ -387,6 +405,7 @@ struct Builder {
             const TwTable *t;
             rc = get_tables(E, tf, ilog2(n), &t);
             if (rc) return rc;
+            o.alu = t->mc.form;                 // one launch holds one arithmetic form
             ++limb_ntts;
         } else if (m.iconn == 1 || m.iconn == 2) {
             src_reg = rd(1);
@@ -675,6 +694,21 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
         for (size_t c = i; c < j;) {
             const size_t cnt = std::min(max_jobs, j - c);
             Launch L{h.kind, h.alu, h.n, (u32)cnt, tables.size()};
+            if (h.kind == K_NTT && cnt >= 16) {
+                // forward transforms: same-modulus runs of 16 first (they take the TMA-staged row pass,
+                // one tile = one row of 16 polynomials sharing its twiddles), the remainder after them
+                std::map<int, std::vector<size_t>> by_mod;
+                for (size_t t = c; t < c + cnt; ++t) by_mod[ops[order[t]].mod].push_back(order[t]);
+                std::vector<size_t> grouped, rest;
+                for (auto &kv : by_mod) {
+                    const size_t full = kv.second.size() / 16 * 16;
+                    grouped.insert(grouped.end(), kv.second.begin(), kv.second.begin() + full);
+                    rest.insert(rest.end(), kv.second.begin() + full, kv.second.end());
+                }
+                L.ngrouped = (u32)grouped.size();
+                std::copy(grouped.begin(), grouped.end(), order.begin() + c);
+                std::copy(rest.begin(), rest.end(), order.begin() + c + grouped.size());
+            }
             std::vector<std::pair<size_t, const VecOp *>> sop_jobs;
             for (size_t t = c; t < c + cnt; ++t) {
                 const VecOp &o = ops[order[t]];
@@ -703,7 +737,7 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
                     const TwTable *tw;
                     int rc = get_tables(E, o.mod, ilog2(o.n), &tw);
                     if (rc) return rc;
-                    NttJob nj{o.a, o.dst, o.kind == K_NTT ? tw->fwd : tw->inv, tw->mc};
+                    NttJob nj{o.a, o.dst, o.kind == K_NTT ? tw->fwd : tw->inv, o.kind == K_NTT ? tw->fwd_rows : nullptr, tw->mc};
                     nj.mc.pre = o.pre;
                     append(tables, nj);
                     break;
@@ -761,8 +795,8 @@ int issue(aloha *E, const Plan &plan, u64 *launched) {
         case K_AUTMAC: e = launch_autmac((const AutMacJob *)tab, L.njobs, L.n, E->stream); break;
         case K_VAUT: e = launch_vaut((const PermJob *)tab, L.njobs, L.n, E->stream); break;
         case K_VROLI: e = launch_vroli((const PermJob *)tab, L.njobs, L.n, E->stream); break;
-        case K_NTT: e = launch_ntt_forward((const NttJob *)tab, L.njobs, ilog2(L.n), E->stream); break;
-        case K_INTT: e = launch_ntt_inverse((const NttJob *)tab, L.njobs, ilog2(L.n), E->stream); break;
+        case K_NTT: e = launch_ntt_forward((const NttJob *)tab, L.njobs, L.ngrouped, ilog2(L.n), L.alu, E->stream); break;
+        case K_INTT: e = launch_ntt_inverse((const NttJob *)tab, L.njobs, ilog2(L.n), L.alu, E->stream); break;
         }
         if (e != cudaSuccess) {
             E->last_error = std::string("kernel launch: ") + cudaGetErrorString(e);

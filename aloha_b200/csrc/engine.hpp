@@ -60,10 +60,12 @@ struct Launch {
     OpKind kind;
     u32 alu, n, njobs;
     size_t table_off;   // byte offset of the job table inside the plan's device buffer
+    u32 ngrouped = 0;   // K_NTT: leading jobs arranged in same-modulus runs of 16 (kernels.cuh launch_ntt_forward)
 };
 
 struct TwTable {
     Tw *fwd = nullptr, *inv = nullptr;
+    Tw *fwd_rows = nullptr;   // forward twiddles in the row pass's read order (kernels.cuh row_slot)
     ModulusConsts mc{};
 };
 

@@ -11,17 +11,30 @@ namespace alb {
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
-// Twiddle entry: {w, floor(w * 2^64 / q)}.  Forward table index j holds psi^bitrev(j, logN)
-// (reference order: sim/vp/tf_rom_generator/tf_rom_generator.sv:28-30,111), inverse table the same
-// with psi^-1 (:61-63,147-148).
+// Twiddle entry {w, wp}.  Forward table index j holds w = psi^bitrev(j, logN) (reference order:
+// sim/vp/tf_rom_generator/tf_rom_generator.sv:28-30,111), inverse table the same with psi^-1
+// (:61-63,147-148).  The companion word depends on the modulus form (below):
+//   FORM_GENERIC : wp = floor(w * 2^64 / q)   (Shoup quotient)
+//   FORM_PM      : wp = w * 2^32 mod q        (second half of the split product, modarith.cuh mul_pm)
 struct __align__(16) Tw { u64 w, wp; };
+
+// How the transform kernels multiply modulo q.  Chosen per modulus when its tables are built; one launch
+// only ever holds jobs of one form.
+enum ModForm : u32 {
+    FORM_GENERIC = 0,      // any 60-bit prime: Shoup / Harvey, 10 IMAD per product
+    FORM_PM = 1            // q = 2^60 - d with d <= 2^27 (pseudo-Mersenne): split product + one fold, 5 IMAD
+};
 
 struct ModulusConsts {
     u64 q;
-    u64 ninv, ninv_p;      // N^-1 mod q (Shoup pair)            -- inverse transform, last stage
-    u64 wninv, wninv_p;    // itw[1] * N^-1 mod q (Shoup pair)
-    u32 mest;              // floor(2^91 / q)
+    u64 ninv, ninv_p;      // N^-1 mod q as a twiddle pair         -- inverse transform, last stage
+    u64 wninv, wninv_p;    // itw[1] * N^-1 mod q as a twiddle pair
+    u32 mest;              // floor(2^91 / q)                      (FORM_GENERIC)
     u32 pre;               // element-wise op folded into the transform's load: 0 none, 1 VCPY, 2 VFQMOD
+    u32 form;              // ModForm
+    u32 d;                 // 2^60 - q                             (FORM_PM)
+    u64 q3;                // 3q, the butterfly's subtraction offset (FORM_PM).  Loaded, not computed: ptxas
+                           // otherwise re-derives it from q inside every butterfly (IMAD.WIDE by 3 + negation)
 };
 enum NttPre : u32 { PRE_NONE = 0, PRE_VCPY = 1, PRE_VFQMOD = 2 };
 
@@ -30,8 +43,16 @@ struct NttJob {
     const u64 *src;
     u64 *dst;
     const Tw *tw;          // forward or inverse table for (modulus, N)
+    const Tw *rtw;         // the same twiddles in the row kernels' read order, 256 entries per row of the
+                           // N/256 x 256 view: what one TMA copy stages for a tile (ntt_kernels.cu, row_slot)
     ModulusConsts mc;
 };
+// Slot of twiddle (level u, index j < 2^u) inside a row's 256-entry block of `rtw` (slot 0 unused).
+// Levels 0..3 are warp-uniform reads; levels 4..7 are read by lane h = j >> (u-4) with m = j mod 2^(u-4)
+// and are laid out [m][h] so that the 16 lanes of a half-warp read 16 consecutive entries.
+__host__ __device__ constexpr u32 row_slot(u32 u, u32 j) {
+    return u < 4 ? (1u << u) + j : (1u << u) + (j & ((1u << (u - 4)) - 1)) * 16 + (j >> (u - 4));
+}
 
 // Element-wise modalu op over n words.
 struct EwJob {
@@ -101,8 +122,11 @@ struct AutMacJob {
     u64 q, iq, k, kinv;
 };
 
-cudaError_t launch_ntt_forward(const NttJob *jobs_dev, u32 njobs, u32 logn, cudaStream_t st);
-cudaError_t launch_ntt_inverse(const NttJob *jobs_dev, u32 njobs, u32 logn, cudaStream_t st);
+// every job of one launch has mc.form == form.  The first `ngrouped` jobs (a multiple of 16) are arranged
+// in runs of 16 that share one modulus: their row pass runs as the TMA-staged persistent kernel, one
+// tile = the same row of 16 polynomials, twiddles staged once per tile.
+cudaError_t launch_ntt_forward(const NttJob *jobs_dev, u32 njobs, u32 ngrouped, u32 logn, u32 form, cudaStream_t st);
+cudaError_t launch_ntt_inverse(const NttJob *jobs_dev, u32 njobs, u32 logn, u32 form, cudaStream_t st);
 cudaError_t launch_ew(u32 alu_op, const EwJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
 cudaError_t launch_vaut(const PermJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
 cudaError_t launch_vroli(const PermJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);

@@ -109,4 +109,40 @@ __device__ __forceinline__ u64 reduce_full(u64 x, u64 q, u64 nq, u32 mest) {
     return csub_s(((u64)hi << 32) | (u32)r, q);
 }
 
+// ---- pseudo-Mersenne moduli: q = 2^60 - d, d <= 2^27 ----------------------------------------------
+// (the synthetic configs' prime rule -- scan down from 2^60 with q = 1 mod 2N -- only produces these)
+// With the twiddle stored as the pair {w, w * 2^32 mod q} the product w*y splits into two 60x32-bit
+// halves, T = w * y_lo + (w 2^32 mod q) * y_hi < 2^93, and T mod q needs ONE fold at 2^61 = 2d (mod q):
+// 5 IMAD.WIDE per modular multiplication against Shoup's 10, for ANY 64-bit y.  Result in [0, 3q):
+//   T >> 61 <= 2^32 - 2, so the fold is < 2^61 + 2^33 d - 4d <= 3 * 2^60 - 4d < 3q for d <= 2^27.
+__device__ __forceinline__ u64 mul_pm(u64 y, u64 w, u64 w2, u32 d2) {
+    u64 r;
+    asm("{\n\t.reg .u64 X, B, U, C;\n\t.reg .u32 xl, xh, u0, u1, y0, y1, rh, m;\n\t"
+        "mul.wide.u32 U, %5, %2;\n\t"          // U = w_hi * y_lo            (< 2^60)
+        "mad.wide.u32 U, %6, %4, U;\n\t"       //   + w2_hi * y_hi           (< 2^61)
+        "mov.b64 {u0, u1}, U;\n\t"
+        "mul.wide.u32 X, %1, %2;\n\t"          // X = w_lo * y_lo
+        "mul.wide.u32 B, %3, %4;\n\t"
+        "add.cc.u64 X, X, B;\n\t"              //   + w2_lo * y_hi           (carry = 2^64)
+        "addc.u32 u1, u1, 0;\n\t"
+        "mov.b64 {xl, xh}, X;\n\t"
+        "add.cc.u32 y0, u0, xh;\n\t"           // T = (y1 : y0 : xl)
+        "addc.u32 y1, u1, 0;\n\t"
+        "shf.r.wrap.b32 rh, y0, y1, 29;\n\t"   // T >> 61
+        "and.b32 m, y0, 0x1fffffff;\n\t"
+        "mov.b64 C, {xl, m};\n\t"              // T mod 2^61
+        "mad.wide.u32 %0, rh, %7, C;\n\t}"
+        : "=l"(r)
+        : "r"((u32)w), "r"((u32)y), "r"((u32)w2), "r"((u32)(y >> 32)), "r"((u32)(w >> 32)), "r"((u32)(w2 >> 32)), "r"(d2));
+    return r;
+}
+// any x < 2^64  ->  x mod q in [0, 2^60 + 15 d) (below 2q): fold at 2^60 = d (mod q).
+__device__ __forceinline__ u64 fold_pm(u64 x, u32 d) {
+    u64 r = x & ((1ull << 60) - 1);
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(r) : "r"((u32)(x >> 60)), "r"(d));
+    return r;
+}
+// any x < 2^64  ->  canonical
+__device__ __forceinline__ u64 canon_pm(u64 x, u64 q, u32 d) { return csub_s(fold_pm(x, d), q); }
+
 }  // namespace alb

@@ -209,6 +209,8 @@ def run_gpu(args):
             return e0.elapsed_time(e1)
         if args.only == "keyswitch":
             out = measure_keyswitch(torch, dist, A, {"device": local}, stream, timed0, world, rank)
+        elif args.only == "tv":
+            out = measure_tv_latency(A) if rank == 0 else None
         else:
             out = measure_rotmac(torch, A, asm, {"device": local}, primes, psis, stream, timed0, 16)
         if rank == 0:
@@ -405,28 +407,32 @@ def run_gpu(args):
 
 def measure_tv_latency(A):
     """tv-case latency vs CPU (BASELINE.json metric, second half): the three shipped cases replayed
-    end to end (DMA + every run_vp + the per-op dump read-back) on the GPU engine through the C host
-    driver, and on the oracle single-threaded.  Inputs: tests/golden (committed fixtures)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import golden_util as G
-    from oracle import oracle as O
+    end to end on the GPU engine through the C host driver, and (cpu_baseline leg) on the oracle
+    single-threaded.  Inputs: the committed fixtures under tests/golden (no oracle code on the GPU leg)."""
+    gold = os.path.join(ROOT, "tests", "golden")
+    manifest = json.load(open(os.path.join(gold, "manifest.json")))
+    pool = np.load(os.path.join(gold, "pool.npz"))
+    micro = json.load(open(os.path.join(gold, "microcode.json")))
+    kernels = [(np.frombuffer(bytes.fromhex("".join(k["words"])), dtype=np.uint8).reshape(-1, 12).copy(), k["pc"])
+               for k in micro.values()]
+    dram_vp_base = 10485760                                   # top_noaxilite_tb.sv:45
     out = {}
     for case in ("case0_4_4", "case1_8_8", "case2_16_16"):
-        m = G.manifest()
-        n, entry = m["n"], m["cases"][case]
-        ops, dram, enc, ksk = G.case_inputs(case)
+        n, entry = manifest["n"], manifest["cases"][case]
+        prog_lines = entry["program"]
+        dram_addr = {i: (int(l.split(",")[1], 16) << 32) | int(l.split(",")[2], 16) for i, l in enumerate(prog_lines)}
 
         def gpu_once(flags=0, dumps=True):
             eng = A.Engine(flags=flags)
-            for words, pc in G.microcode():
+            for words, pc in kernels:
                 eng.load_isram(words, pc)
-            for row, data in ksk.items():
-                eng.dma_ksk_h2d(row, data)
-            host = A.HostDriver(eng, "\n".join(entry["program"]), n)
+            for row, key in entry["ksk"].items():
+                eng.dma_ksk_h2d(int(row), pool[key])
+            host = A.HostDriver(eng, "\n".join(prog_lines), n)
             for i, key in entry["loads"].items():
-                host.dram_write(O.DRAM_VP_BASE + ops[int(i)].dram_addr, G.pool(key))
-            for i, data in enc.items():
-                host.set_encoder_output(i, data)
+                host.dram_write(dram_vp_base + dram_addr[int(i)], pool[key])
+            for i, key in entry["encoder"].items():
+                host.set_encoder_output(int(i), pool[key])
             eng.sync()
             run = host.run_op if dumps else host.run_op_nodump
             t0 = time.perf_counter()
@@ -441,26 +447,32 @@ def measure_tv_latency(A):
                     run(i)
                 eng.sync()
                 best = min(best, time.perf_counter() - t1)
-            return dt, best, eng.stats()
+            st = eng.stats()
+            eng.close()
+            return dt, best, st
         first, steady, st = gpu_once()
         _, steady_nodump, _ = gpu_once(dumps=False)
         _, steady_graphs, _ = gpu_once(flags=A.F_GRAPHS, dumps=False)
-        _, steady_defer, st_defer = gpu_once(flags=A.F_DEFER | A.F_GRAPHS, dumps=False)
+        out[case] = {"ops": len(prog_lines), "gpu_ms_first_run": 1e3 * first, "gpu_ms_steady": 1e3 * steady,
+                     "gpu_ms_steady_no_dumps": 1e3 * steady_nodump, "gpu_ms_steady_no_dumps_cuda_graphs": 1e3 * steady_graphs,
+                     "kernel_launches_per_pass": st["kernel_launches"] / 6.0,
+                     "note": "gpu_ms_steady includes every per-op DMA and the 256 KiB dump read-back the testbench does "
+                             "after each op; the no_dumps figures run the same ops with one sync at the end"}
+    # cpu_baseline leg: the same replays on the oracle, one thread
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import golden_util as G
+    from oracle import oracle as O
+    for case in out:
+        ops, dram, enc, ksk = G.case_inputs(case)
         model = O.GoldenModel()
         for words, pc in G.microcode():
             model.load_isram(words, pc)
         for row, data in ksk.items():
             model.dma_ksk_h2d(row, data)
         t0 = time.perf_counter()
-        for _ in O.replay(model, ops, dram.copy(), enc, n):
+        for _ in O.replay(model, ops, dram.copy(), enc, manifest["n"]):
             pass
-        cpu = time.perf_counter() - t0
-        out[case] = {"ops": len(ops), "gpu_ms_first_run": 1e3 * first, "gpu_ms_steady": 1e3 * steady,
-                     "gpu_ms_steady_no_dumps": 1e3 * steady_nodump, "gpu_ms_steady_no_dumps_cuda_graphs": 1e3 * steady_graphs,
-                     "gpu_ms_steady_no_dumps_deferred_queue_cuda_graphs": 1e3 * steady_defer,
-                     "kernel_launches_deferred_queue": st_defer["kernel_launches"],
-                     "cpu_oracle_ms_1thread": 1e3 * cpu, "kernel_launches": st["kernel_launches"],
-                     "note": "gpu_ms_steady includes every per-op DMA and the 256 KiB dump read-back the testbench does after each op; the no_dumps figures run the same ops with one sync at the end"}
+        out[case]["cpu_oracle_ms_1thread"] = 1e3 * (time.perf_counter() - t0)
     return out
 
 
@@ -584,7 +596,7 @@ def main():
     ap.add_argument("--chunk-mib", type=int, default=0, help="override the engine's L2 chunk size")
     ap.add_argument("--polys", type=int, default=64)
     ap.add_argument("--no-extra", action="store_true", help="skip the rotate-MAC and key-switch workloads")
-    ap.add_argument("--only", default="", choices=["", "keyswitch", "rotmac"], help="profiling: run one extra workload alone")
+    ap.add_argument("--only", default="", choices=["", "keyswitch", "rotmac", "tv"], help="profiling: run one extra workload alone")
     args = ap.parse_args()
     globals()["POLYS"] = args.polys
     if args.impl == "reference":

@@ -69,9 +69,12 @@ enum {
                                     ops (mul_plain, hom_add, rotate ... of one program) share launches wherever their
                                     data dependencies allow.  Results are identical; an error in a queued call is
                                     reported by the call that flushes it. */
-    ALOHA_F_STRICT = 1u << 4     /* VNTT / VINTT run the RTL's constant-geometry schedule stage by stage with the
+    ALOHA_F_STRICT = 1u << 4,    /* VNTT / VINTT run the RTL's constant-geometry schedule stage by stage with the
                                     RTL ALU: word-exact for ANY input (also >= 2q) and the source register keeps the
                                     ping-pong intermediate the RTL leaves there.  ~10x slower transforms. */
+    ALOHA_F_GENERIC_MODMUL = 1u << 6  /* transforms use the any-prime (Shoup) arithmetic even for moduli of the form
+                                    2^60 - d, d <= 2^27, which otherwise take the cheaper pseudo-Mersenne product.
+                                    Same results; for A/B measurements and tests. */
 };
 
 typedef struct aloha_cfg {

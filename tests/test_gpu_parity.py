@@ -115,6 +115,44 @@ def test_ntt_all_max_inputs_full_size():
     assert (got == O.NttTables(n, primes, psis).batch(x.copy(), np.arange(L))).all()
 
 
+@pytest.mark.parametrize("logn", [8, 9, 12, 13, 16])
+@pytest.mark.parametrize("flags", [0, A.F_GENERIC_MODMUL])
+def test_grouped_row_pass_and_modulus_forms(logn, flags):
+    """19 polynomials x 3 moduli in one launch: per modulus 16 take the TMA-staged row pass and 3 the plain
+    one; two moduli are pseudo-Mersenne (2^60 - d), one is a generic 60-bit prime, so both arithmetic
+    forms run side by side (ALOHA_F_GENERIC_MODMUL forces the generic form for all three).  Every output
+    word against the oracle, inputs include q-1 runs and words in [q, 2q)."""
+    n, B = 1 << logn, 19
+    rp = n // 128
+    primes = O.synthetic_primes(2, 2 * n) + O.synthetic_primes(1, 2 * n, below=(1 << 60) - (1 << 40))
+    assert (1 << 60) - primes[1] <= 1 << 27 < (1 << 60) - primes[2]
+    psis = [O.min_primitive_root(q, 2 * n) for q in primes]
+    L = len(primes)
+    rows = B * L * rp
+    eng = A.Engine(vlmax_bits=n * 64, spm_rows=2 * rows, ksk_rows=0, moduli=list(zip(primes, psis)), flags=flags)
+    eng.load_isram(asm.transform_stream(n, primes).words(), 0)
+    eng.load_isram(asm.transform_stream(n, primes, inverse=True).words(), 1024)
+    rng = np.random.default_rng(1000 + logn)
+    qv = np.array(primes, dtype=np.uint64)[None, :, None]
+    x = rng.integers(0, 1 << 59, (B, L, n), dtype=np.uint64) % qv
+    x[0, :, : n // 2] = qv[0, :, :] - np.uint64(1)
+    x[1, :, n // 2:] += qv[0, :, :]
+    x[18, :, ::3] = qv[0, :, :] - np.uint64(1)
+    eng.dma_mem_h2d(0, x.reshape(-1))
+    s0 = eng.stats()["kernel_launches"]
+    eng.run_vp_batch(0, [(b * L * rp, 0, rows + b * L * rp, 0, 0) for b in range(B)])
+    # columns (if any) + TMA-staged rows + plain rows, once per arithmetic form present in the launch
+    forms = 1 if flags else 2
+    assert eng.stats()["kernel_launches"] - s0 == forms * ((1 if logn > 8 else 0) + 2)
+    F = eng.dma_mem_d2h(rows, B * L * n).reshape(B, L, n)
+    tabs = O.NttTables(n, primes, psis)
+    for b in range(B):
+        assert (F[b] == tabs.batch(x[b].copy(), np.arange(L))).all(), b
+    eng.run_vp_batch(1024, [(rows + b * L * rp, 0, b * L * rp, 0, 0) for b in range(B)])
+    back = eng.dma_mem_d2h(0, B * L * n).reshape(B, L, n)
+    assert (back == x % qv).all()
+
+
 ALU_STREAMS = [("vfqmul", None), ("vfqadd", None), ("vfqsub", None), ("vfqmul", 0x123456789abcdef),
                ("vfqadd", (1 << 60) + 5), ("vfqsub", 77)]
 ALU_CODE = {("vfqmul", False): 0x00, ("vfqadd", False): 0x01, ("vfqsub", False): 0x02,

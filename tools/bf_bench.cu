@@ -15,7 +15,14 @@ __device__ __forceinline__ void ct_bf(u64 &x, u64 &y, const Tw &t, u64 nq, u64 q
     x = xp;
 }
 
-template <int LOGE, int MINB>
+// pseudo-Mersenne butterfly (q = 2^60 - d): 5 IMAD.WIDE, bounds +3q per stage
+__device__ __forceinline__ void ct_bf_pm(u64 &x, u64 &y, const Tw &t, u32 d2, u64 q3) {
+    const u64 m = mul_pm(y, t.w, t.wp, d2);
+    y = x + q3 - m;
+    x = x + m;
+}
+
+template <int LOGE, int MINB, int PM = 0>
 __global__ void __launch_bounds__(256, MINB) k(u64 *io, const Tw *tw, u64 q, int iters) {
     constexpr int E = 1 << LOGE;
     __shared__ Tw stw[256];
@@ -33,32 +40,38 @@ __global__ void __launch_bounds__(256, MINB) k(u64 *io, const Tw *tw, u64 q, int
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 if (e & half) continue;
-                if ((e & (half - 1)) == 0) w = stw[((threadIdx.x + it) & 15) * 16 + (1 << v) + (e >> (LOGE - v))];
-                ct_bf(x[e], x[e + half], w, nq, q2);
+                if ((e & (half - 1)) == 0) w = stw[(((threadIdx.x >> 5) + it) & 15) * 16 + (1 << v) + (e >> (LOGE - v))];   // warp-uniform: a broadcast, no bank conflicts
+                if (PM) ct_bf_pm(x[e], x[e + half], w, (u32)(2 * nq), 3 * q);   // nq = 2^64 - q = 16 d ... only timing matters here
+                else ct_bf(x[e], x[e + half], w, nq, q2);
             }
         }
+        if (PM) {
 #pragma unroll
-        for (int i = 0; i < E; ++i) x[i] = csub_s(x[i], q8);
+            for (int i = 0; i < E; i += 2) x[i] = fold_pm(x[i], (u32)(nq >> 4));     // upper inputs only, as the kernels do
+        } else {
+#pragma unroll
+            for (int i = 0; i < E; ++i) x[i] = csub_s(x[i], q8);
+        }
     }
     for (int i = 0; i < E; ++i) io[t + i * gridDim.x * blockDim.x] = x[i];
 }
 
-template <int LOGE, int MINB>
+template <int LOGE, int MINB, int PM = 0>
 void run(int sms, int clk_khz, u64 *io, Tw *tw, u64 q) {
     const int iters = 2000, E = 1 << LOGE;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, k<LOGE, MINB>);
+    cudaFuncGetAttributes(&fa, k<LOGE, MINB, PM>);
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k<LOGE, MINB>, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k<LOGE, MINB, PM>, 256, 0);
     const int blocks = sms * occ;
-    k<LOGE, MINB><<<blocks, 256>>>(io, tw, q, iters);
+    k<LOGE, MINB, PM><<<blocks, 256>>>(io, tw, q, iters);
     cudaDeviceSynchronize();
-    cudaEventRecord(e0); k<LOGE, MINB><<<blocks, 256>>>(io, tw, q, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventRecord(e0); k<LOGE, MINB, PM><<<blocks, 256>>>(io, tw, q, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     const double bf = (double)blocks * 256 * (E / 2 * LOGE) * iters;
-    printf("E=%2d minb=%d regs=%3d occ=%d CTA/SM (%2d warps): %.2f bf/clk/SM -> %.2f M limb-NTT/s ceiling\n", E, MINB,
+    printf("%s E=%2d minb=%d regs=%3d occ=%d CTA/SM (%2d warps): %.2f bf/clk/SM -> %.2f M limb-NTT/s ceiling\n", PM ? "pseudo-Mersenne" : "Shoup          ", E, MINB,
            fa.numRegs, occ, occ * 8, bf / (ms * 1e-3) / (clk_khz * 1e3) / sms, bf / (ms * 1e-3) / 524288 / 1e6);
 }
 
@@ -78,6 +91,11 @@ int main() {
     run<4, 2>(sms, clk_khz, io, tw, q);
     run<4, 3>(sms, clk_khz, io, tw, q);
     run<4, 4>(sms, clk_khz, io, tw, q);
+    run<4, 1, 1>(sms, clk_khz, io, tw, q);
+    run<4, 2, 1>(sms, clk_khz, io, tw, q);
+    run<4, 3, 1>(sms, clk_khz, io, tw, q);
+    run<4, 4, 1>(sms, clk_khz, io, tw, q);
+    run<3, 4, 1>(sms, clk_khz, io, tw, q);
     run<3, 2>(sms, clk_khz, io, tw, q);
     run<3, 4>(sms, clk_khz, io, tw, q);
     run<3, 6>(sms, clk_khz, io, tw, q);
