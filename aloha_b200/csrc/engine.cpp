@@ -697,15 +697,15 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
             if (h.kind == K_NTT && cnt >= 16) {
                 // forward transforms: same-modulus runs of 16 first (they take the TMA-staged row pass,
                 // one tile = one row of 16 polynomials sharing its twiddles), the remainder after them
-                std::map<int, std::vector<size_t>> by_mod;
-                for (size_t t = c; t < c + cnt; ++t) by_mod[ops[order[t]].mod].push_back(order[t]);
+                std::map<std::pair<int, u32>, std::vector<size_t>> by_mod;
+                for (size_t t = c; t < c + cnt; ++t) by_mod[{ops[order[t]].mod, ops[order[t]].pre}].push_back(order[t]);
                 std::vector<size_t> grouped, rest;
                 for (auto &kv : by_mod) {
                     const size_t full = kv.second.size() / 16 * 16;
                     grouped.insert(grouped.end(), kv.second.begin(), kv.second.begin() + full);
                     rest.insert(rest.end(), kv.second.begin() + full, kv.second.end());
                 }
-                L.ngrouped = (u32)grouped.size();
+                L.ngroups = (u32)(grouped.size() / 16);
                 std::copy(grouped.begin(), grouped.end(), order.begin() + c);
                 std::copy(rest.begin(), rest.end(), order.begin() + c + grouped.size());
             }
@@ -742,6 +742,20 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
                     append(tables, nj);
                     break;
                 }
+                }
+            }
+            if (L.ngroups) {                   // group records of the TMA-staged row pass, after the job table
+                L.group_off = tables.size();
+                for (u32 g = 0; g < L.ngroups; ++g) {
+                    NttRowGroup G{};
+                    const NttJob *nj = reinterpret_cast<const NttJob *>(tables.data() + L.table_off) + 16 * g;
+                    for (int k = 0; k < 16; ++k) {
+                        G.src[k] = h.n == 256 ? nj[k].src : nj[k].dst;
+                        G.dst[k] = nj[k].dst;
+                    }
+                    G.rtw = nj[0].rtw;
+                    G.mc = nj[0].mc;
+                    append(tables, G);
                 }
             }
             for (auto &sj : sop_jobs) {       // operand-pointer lists go right after the launch's job table
@@ -795,7 +809,7 @@ int issue(aloha *E, const Plan &plan, u64 *launched) {
         case K_AUTMAC: e = launch_autmac((const AutMacJob *)tab, L.njobs, L.n, E->stream); break;
         case K_VAUT: e = launch_vaut((const PermJob *)tab, L.njobs, L.n, E->stream); break;
         case K_VROLI: e = launch_vroli((const PermJob *)tab, L.njobs, L.n, E->stream); break;
-        case K_NTT: e = launch_ntt_forward((const NttJob *)tab, L.njobs, L.ngrouped, ilog2(L.n), L.alu, E->stream); break;
+        case K_NTT: e = launch_ntt_forward((const NttJob *)tab, L.njobs, (const NttRowGroup *)(base + L.group_off), L.ngroups, ilog2(L.n), L.alu, E->stream); break;
         case K_INTT: e = launch_ntt_inverse((const NttJob *)tab, L.njobs, ilog2(L.n), L.alu, E->stream); break;
         }
         if (e != cudaSuccess) {

@@ -60,7 +60,8 @@ struct Launch {
     OpKind kind;
     u32 alu, n, njobs;
     size_t table_off;   // byte offset of the job table inside the plan's device buffer
-    u32 ngrouped = 0;   // K_NTT: leading jobs arranged in same-modulus runs of 16 (kernels.cuh launch_ntt_forward)
+    u32 ngroups = 0;    // K_NTT: the first 16 * ngroups jobs are same-modulus runs of 16, described by the
+    size_t group_off = 0;   //        NttRowGroup records at this offset (kernels.cuh launch_ntt_forward)
 };
 
 struct TwTable {

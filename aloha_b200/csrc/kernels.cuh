@@ -122,10 +122,22 @@ struct AutMacJob {
     u64 q, iq, k, kinv;
 };
 
-// every job of one launch has mc.form == form.  The first `ngrouped` jobs (a multiple of 16) are arranged
-// in runs of 16 that share one modulus: their row pass runs as the TMA-staged persistent kernel, one
-// tile = the same row of 16 polynomials, twiddles staged once per tile.
-cudaError_t launch_ntt_forward(const NttJob *jobs_dev, u32 njobs, u32 ngrouped, u32 logn, u32 form, cudaStream_t st);
+// 16 forward jobs that share a modulus (and load op), as the TMA-staged row pass wants them: one record
+// is one bulk copy.  `src` is what the row pass reads: the column pass's output (= dst), or the job's
+// source when N = 256 and there is no column pass.
+struct __align__(16) NttRowGroup {
+    const u64 *src[16];
+    u64 *dst[16];
+    const Tw *rtw;
+    u64 pad;
+    ModulusConsts mc;
+};
+
+// every job of one launch has mc.form == form.  The first 16 * ngroups jobs are also described by
+// `groups_dev` (runs of 16 jobs sharing a modulus): their row pass runs as the TMA-staged persistent
+// kernel, one tile = the same row of 16 polynomials, twiddles staged once per tile.
+cudaError_t launch_ntt_forward(const NttJob *jobs_dev, u32 njobs, const NttRowGroup *groups_dev, u32 ngroups, u32 logn,
+                               u32 form, cudaStream_t st);
 cudaError_t launch_ntt_inverse(const NttJob *jobs_dev, u32 njobs, u32 logn, u32 form, cudaStream_t st);
 cudaError_t launch_ew(u32 alu_op, const EwJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
 cudaError_t launch_vaut(const PermJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);

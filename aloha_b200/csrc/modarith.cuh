@@ -100,14 +100,15 @@ __device__ __forceinline__ u64 mul_shoup(u64 y, u64 w, u64 wp, u64 nq) { return 
 
 // x < 2^64, q in (2^59, 2^60), mest = floor(2^91 / q) (32 bits).  floor(x/q) - 1 <= est <= floor(x/q),
 // so x - est*q is in [0, 2q); one conditional subtract makes it canonical.
-__device__ __forceinline__ u64 reduce_full(u64 x, u64 q, u64 nq, u32 mest) {
+__device__ __forceinline__ u64 reduce_lazy(u64 x, u64 nq, u32 mest) {     // -> [0, 2q)
     const u32 est = __umulhi((u32)(x >> 32), mest) >> 27;
     u64 r = x;
     asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(r) : "r"(est), "r"((u32)nq));
     u32 hi = (u32)(r >> 32);
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(est), "r"((u32)(nq >> 32)));
-    return csub_s(((u64)hi << 32) | (u32)r, q);
+    return ((u64)hi << 32) | (u32)r;
 }
+__device__ __forceinline__ u64 reduce_full(u64 x, u64 q, u64 nq, u32 mest) { return csub_s(reduce_lazy(x, nq, mest), q); }
 
 // ---- pseudo-Mersenne moduli: q = 2^60 - d, d <= 2^27 ----------------------------------------------
 // (the synthetic configs' prime rule -- scan down from 2^60 with q = 1 mod 2N -- only produces these)
@@ -135,6 +136,30 @@ __device__ __forceinline__ u64 mul_pm(u64 y, u64 w, u64 w2, u32 d2) {
         : "=l"(r)
         : "r"((u32)w), "r"((u32)y), "r"((u32)w2), "r"((u32)(y >> 32)), "r"((u32)(w >> 32)), "r"((u32)(w2 >> 32)), "r"(d2));
     return r;
+}
+
+// The same product left in two pieces, w*y mod q = P + L with P = (T >> 61) * 2d and L = T mod 2^61 (both
+// below 2^61): the forward butterfly adds them as separate operands, x' = x + P + L and
+// y' = (x + 3q - P) - L, which ptxas turns into 3-input IADD3 / IADD3.X pairs -- two instructions fewer
+// per butterfly than assembling the product first, and none of the carry adds lands on the IMAD pipe.
+__device__ __forceinline__ void mul_pm_parts(u64 y, u64 w, u64 w2, u32 d2, u64 &P, u64 &L) {
+    u32 xl, y0, y1;
+    asm("{\n\t.reg .u64 X, B, U;\n\t.reg .u32 xh, u0, u1;\n\t"
+        "mul.wide.u32 U, %7, %4;\n\t"
+        "mad.wide.u32 U, %8, %6, U;\n\t"
+        "mov.b64 {u0, u1}, U;\n\t"
+        "mul.wide.u32 X, %3, %4;\n\t"
+        "mul.wide.u32 B, %5, %6;\n\t"
+        "add.cc.u64 X, X, B;\n\t"
+        "addc.u32 u1, u1, 0;\n\t"
+        "mov.b64 {%0, xh}, X;\n\t"
+        "add.cc.u32 %1, u0, xh;\n\t"
+        "addc.u32 %2, u1, 0;\n\t}"
+        : "=r"(xl), "=r"(y0), "=r"(y1)
+        : "r"((u32)w), "r"((u32)y), "r"((u32)w2), "r"((u32)(y >> 32)), "r"((u32)(w >> 32)), "r"((u32)(w2 >> 32)));
+    const u32 rh = __funnelshift_r(y0, y1, 29);
+    P = (u64)rh * d2;
+    L = ((u64)(y0 & 0x1fffffffu) << 32) | xl;
 }
 // any x < 2^64  ->  x mod q in [0, 2^60 + 15 d) (below 2q): fold at 2^60 = d (mod q).
 __device__ __forceinline__ u64 fold_pm(u64 x, u32 d) {

@@ -38,6 +38,12 @@
 #ifndef COLS_MINB
 #define COLS_MINB 3
 #endif
+#ifndef ROWS_TMA_MINB
+#define ROWS_TMA_MINB 2
+#endif
+#ifndef ROWS_TMA_STAGES
+#define ROWS_TMA_STAGES 3
+#endif
 
 namespace alb {
 
@@ -77,6 +83,7 @@ template <> struct Arith<FORM_GENERIC> {
         return x;
     }
     __device__ __forceinline__ u64 canon(u64 x) const { return reduce_full(x, q, nq, mest); }   // any word
+    __device__ __forceinline__ u64 canon_lazy(u64 x) const { return reduce_lazy(x, nq, mest); } // any word -> below 2q
     __device__ __forceinline__ u64 canon_mul(u64 x) const { return csub_s(x, q); }              // a product
     __device__ __forceinline__ u64 off(int b) const { return b <= 2 ? q2 : b <= 4 ? q4 : q8; }
 };
@@ -90,13 +97,15 @@ template <> struct Arith<FORM_PM> {
         : q(mc.q), q2(2 * mc.q), q3(mc.q3), q4(4 * mc.q), q8(8 * mc.q), d(mc.d), d2(2 * mc.d) {}
     __device__ __forceinline__ u64 mul(u64 y, u64 w, u64 wp) const { return mul_pm(y, w, wp, d2); }
     __device__ __forceinline__ void ct(u64 &x, u64 &y, const Tw &t) const {
-        const u64 m = mul_pm(y, t.w, t.wp, d2);
-        y = x + q3 - m;
-        x = x + m;
+        u64 P, L;
+        mul_pm_parts(y, t.w, t.wp, d2, P, L);
+        y = (x + q3 - P) - L;
+        x = x + P + L;
     }
     __device__ __forceinline__ u64 red(u64 x) const { return fold_pm(x, d); }
     __device__ __forceinline__ u64 norm(u64 x, int b) const { return b > 2 ? fold_pm(x, d) : x; }
     __device__ __forceinline__ u64 canon(u64 x) const { return canon_pm(x, q, d); }
+    __device__ __forceinline__ u64 canon_lazy(u64 x) const { return fold_pm(x, d); }
     __device__ __forceinline__ u64 canon_mul(u64 x) const { return canon_pm(x, q, d); }
     __device__ __forceinline__ u64 off(int b) const { return b <= 2 ? q2 : b <= 4 ? q4 : q8; }
 };
@@ -258,18 +267,23 @@ __global__ void __launch_bounds__(256, ROWS_MINB) ntt_fwd_rows(const NttJob *__r
 
 // ============================================================================ forward: rows, TMA-staged
 // Persistent variant of the row pass for launches that hold many polynomials per modulus (the batched
-// configs).  One tile = row r of 16 polynomials that share a modulus (jobs[16 g .. 16 g + 15]): the 16
-// rows (16 x 2 KiB), the row's 256 twiddles in read order (4 KiB, NttJob::rtw) and the group's job
-// records are staged in shared memory by cp.async.bulk (TMA) into a two-stage ring, each stage armed
-// with an mbarrier, so the loads of tile i+1 run under the butterflies of tile i.  The twiddles of a
-// tile are read from shared memory by all 16 half-warps instead of 16 times from L1/L2.
+// configs).  One tile = row r of 16 polynomials that share a modulus (one NttRowGroup): the 16 rows
+// (16 x 2 KiB), the row's 256 twiddles in read order (4 KiB, NttJob::rtw) and the group record are staged
+// in shared memory by cp.async.bulk (TMA) into a ring of kStages stages, each armed with an mbarrier, so
+// the loads of tile i+kStages run under the butterflies of the tiles before it.  There is no block-wide
+// barrier: a warp that is done with a stage's shared memory counts itself out, and the last one out
+// refills the stage.  The twiddles of a tile are read from shared memory by all 16 half-warps instead of
+// 16 times from L1/L2, and the mid-transform exchange happens in place in the half-warp's own staged row
+// (XOR-swizzled 16-byte chunks instead of padding): 36.3 KiB per stage, two CTAs per SM.
+constexpr int kStages = ROWS_TMA_STAGES;
 struct RowsSmem {
-    u64 data[2][16][256];
-    Tw tw[2][256];
-    NttJob jobs[2][16];
-    u64 xbuf[16 * kRowPad];
-    u64 bar[2];
+    u64 data[kStages][16][256];
+    Tw tw[kStages][256];
+    NttRowGroup grp[kStages];
+    u64 full[kStages];
+    u32 done[kStages];
 };
+static_assert(sizeof(RowsSmem) <= (233472 - ROWS_TMA_MINB * 1024) / ROWS_TMA_MINB, "ROWS_TMA_MINB CTAs per SM");
 
 __device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
@@ -301,78 +315,97 @@ __device__ __forceinline__ Tw ldtw_s(const Tw *p) {
 #undef ALOHA_LDTW
 #define ALOHA_LDTW ldtw_s
 template <int S1, int FORM>
-__global__ void __launch_bounds__(256, 2) ntt_fwd_rows_tma(const NttJob *__restrict__ jobs, u32 ntiles) {
+__global__ void __launch_bounds__(256, ROWS_TMA_MINB) ntt_fwd_rows_tma(const NttRowGroup *__restrict__ groups, u32 ntiles) {
     typedef Arith<FORM> AR;
     constexpr int R = 1 << S1;
-    constexpr u32 kStageBytes = 16 * 2048 + 256 * sizeof(Tw) + 16 * sizeof(NttJob);
+    constexpr u32 kStageBytes = 16 * 2048 + 256 * sizeof(Tw) + sizeof(NttRowGroup);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RowsSmem &S = *reinterpret_cast<RowsSmem *>(smem_raw);
-    const int t = threadIdx.x, hw = t >> 4, h = t & 15;
+    const int t = threadIdx.x, lane = t & 31, hw = t >> 4, h = t & 15;
     if (t == 0) {
-        mbar_init(&S.bar[0], 1);
-        mbar_init(&S.bar[1], 1);
+        for (int b = 0; b < kStages; ++b) {
+            mbar_init(&S.full[b], 1);
+            S.done[b] = 0;
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // warp 0: arm stage b and start the copies of `tile` into it
+    // one whole warp: arm stage b and start the copies of `tile` into it
     auto stage_in = [&](u32 tile, int b) {
-        const u32 g = tile / R, r = tile % R;
-        if (t == 0) mbar_arrive_expect_tx(&S.bar[b], kStageBytes);
+        const NttRowGroup *G = groups + tile / R;
+        const size_t off = (size_t)(tile % R) * 256;
+        if (lane == 0) mbar_arrive_expect_tx(&S.full[b], kStageBytes);
         __syncwarp();
-        const NttJob *grp = jobs + 16 * g;
-        if (t < 16) {
-            const u64 *src = (S1 == 0 ? grp[t].src : grp[t].dst) + (size_t)r * 256;
-            bulk_g2s(&S.data[b][t][0], src, 2048, &S.bar[b]);
-        } else if (t == 16) {
-            bulk_g2s(&S.tw[b][0], grp[0].rtw + (size_t)r * 256, 256 * sizeof(Tw), &S.bar[b]);
-        } else if (t == 17) {
-            bulk_g2s(&S.jobs[b][0], grp, 16 * sizeof(NttJob), &S.bar[b]);
-        }
+        if (lane < 16) bulk_g2s(&S.data[b][lane][0], G->src[lane] + off, 2048, &S.full[b]);
+        else if (lane == 16) bulk_g2s(&S.tw[b][0], G->rtw + off, 256 * sizeof(Tw), &S.full[b]);
+        else if (lane == 17) bulk_g2s(&S.grp[b], G, sizeof(NttRowGroup), &S.full[b]);
     };
+    const u32 stride = gridDim.x;
     u32 tile = blockIdx.x;
-    if (t < 32 && tile < ntiles) stage_in(tile, 0);
-    u64 *buf = S.xbuf + hw * kRowPad;
-    for (u32 i = 0; tile < ntiles; ++i, tile += gridDim.x) {
-        const int b = i & 1;
-        // every thread left stage b^1 at the barrier that closed the previous iteration
-        if (t < 32 && tile + gridDim.x < ntiles) stage_in(tile + gridDim.x, b ^ 1);
-        mbar_wait(&S.bar[b], (i >> 1) & 1);
-        const NttJob &job = S.jobs[b][hw];
-        const AR A(job.mc);
-        u64 *dst = job.dst + (size_t)(tile % R) * 256;
+    if (t < 32) {
+        for (int b = 0; b < kStages; ++b)
+            if (tile + b * stride < ntiles) stage_in(tile + b * stride, b);
+    }
+    for (u32 i = 0, b = 0, parity = 0; tile < ntiles; ++i, tile += stride) {
+        mbar_wait(&S.full[b], parity);
+        const NttRowGroup &G = S.grp[b];
+        const AR A(G.mc);
+        u64 *dst = G.dst[hw] + (size_t)(tile % R) * 256;
         const Tw *tw = S.tw[b];
+        u64 *row = &S.data[b][hw][0];
 
         u64 x[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = S.data[b][hw][h + 16 * k];
-        if (S1 == 0 && job.mc.pre) {
+        for (int k = 0; k < 16; ++k) x[k] = row[h + 16 * k];
+        __syncwarp();                      // the row is in registers: its 2 KiB are the exchange buffer now
+        if (S1 == 0 && G.mc.pre) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) x[k] = apply_pre(x[k], job.mc.pre, A);
+            for (int k = 0; k < 16; ++k) x[k] = apply_pre(x[k], G.mc.pre, A);
         }
         int B = cols_out_bound<FORM>(S1);
         // phase A: level u pairs k-bit (3-u); twiddle j = k >> (4 - u), warp-uniform
 #pragma unroll
         for (int u = 0; u < 4; ++u) ALOHA_CT_STAGE(16, 8 >> u, row_slot(u, g0 >> (4 - u)))
+        // exchange h + 16 k -> 16 h + e.  Word (k, h) lives in 128-byte line k, 16-byte chunk (h/2) ^ (k mod 8):
+        // the 16 lanes write one whole line, and the 8 lanes of an LDS.128 phase read 8 different chunks.
 #pragma unroll
-        for (int k = 0; k < 16; ++k) buf[h + 18 * k] = x[k];
+        for (int k = 0; k < 16; ++k) row[16 * k + ((((h >> 1) ^ (k & 7)) << 1) | (h & 1))] = x[k];
         __syncwarp();
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
-            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(buf + 18 * h + e);
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(row + 16 * h + (((e >> 1) ^ (h & 7)) << 1));
             x[e] = v.x;
             x[e + 1] = v.y;
         }
         // phase B: level u pairs e-bit (7-u); twiddle j = (16 h + e) >> (8 - u)
 #pragma unroll
         for (int u = 4; u < 8; ++u) ALOHA_CT_STAGE(16, 128 >> u, row_slot(u, (16 * h + g0) >> (8 - u)))
+        // Done with stage b's shared memory (the results are in registers).  Its rows were written through
+        // the generic proxy: order that before the TMA that refills them.  The last warp out resets the
+        // count and stages the tile kStages steps ahead.  This comes BEFORE the global stores, so the
+        // fence does not wait for them.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        u32 last = 0;
+        if (lane == 0) {
+            last = atomicAdd(&S.done[b], 1u) == 7u;
+            if (last) S.done[b] = 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && tile + kStages * stride < ntiles) stage_in(tile + kStages * stride, b);
+        // all eight 16-byte values first, then the stores: distinct register quads, so no store waits for
+        // the previous one to release its source registers
+        // 16-byte stores whose four words are selected straight into the store's register quad
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
-            ulonglong2 v;
-            v.x = A.canon(x[e]);
-            v.y = A.canon(x[e + 1]);
-            *reinterpret_cast<ulonglong2 *>(dst + 16 * h + e) = v;
+            const u64 a0 = A.canon_lazy(x[e]), a1 = A.canon_lazy(x[e + 1]);     // below 2q
+            const u64 b0 = a0 - A.q, b1 = a1 - A.q;
+            const bool n0 = (long long)b0 < 0, n1 = (long long)b1 < 0;
+            const u32 w0 = n0 ? (u32)a0 : (u32)b0, w1 = n0 ? (u32)(a0 >> 32) : (u32)(b0 >> 32);
+            const u32 w2 = n1 ? (u32)a1 : (u32)b1, w3 = n1 ? (u32)(a1 >> 32) : (u32)(b1 >> 32);
+            asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 16 * h + e), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
         }
-        __syncthreads();
+        if (++b == kStages) { b = 0; parity ^= 1; }
     }
 }
 #undef ALOHA_LDTW
@@ -535,19 +568,19 @@ unsigned long long g_launches = 0;
 unsigned long long kernel_launch_count() { return g_launches; }
 static inline void count_launch() { ++g_launches; }
 
-static int persistent_ctas() {            // two resident CTAs per SM of the current device
+static int sm_count() {
     static int n = 0;
     if (!n) {
-        int dev = 0, sms = 0;
+        int dev = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        n = 2 * (sms > 0 ? sms : 148);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
     }
     return n;
 }
 
 template <int S1, int FORM>
-static cudaError_t fwd_impl(const NttJob *jobs, u32 njobs, u32 ngrouped, cudaStream_t st) {
+static cudaError_t fwd_impl(const NttJob *jobs, u32 njobs, const NttRowGroup *groups, u32 ngroups, cudaStream_t st) {
     constexpr int R = 1 << S1;
     if constexpr (S1 > 0) {
         constexpr int LA = S1 < 4 ? S1 : 4, H = R >> LA;
@@ -555,28 +588,28 @@ static cudaError_t fwd_impl(const NttJob *jobs, u32 njobs, u32 ngrouped, cudaStr
         ntt_fwd_cols<S1, FORM><<<njobs * H, 256, smem, st>>>(jobs);
         count_launch();
     }
-    if (ngrouped) {
-        static bool attr_set = false;
-        if (!attr_set) {
+    if (ngroups) {
+        static int resident = 0;            // CTAs of the persistent row pass that fit on one SM
+        if (!resident) {
             cudaError_t e = cudaFuncSetAttribute(ntt_fwd_rows_tma<S1, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmem));
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ntt_fwd_rows_tma<S1, FORM>, 256, sizeof(RowsSmem));
             if (e != cudaSuccess) return e;
-            attr_set = true;
+            if (resident < 1) return cudaErrorLaunchOutOfResources;
         }
-        const u32 tiles = ngrouped / 16 * R;
-        const u32 grid = tiles < (u32)persistent_ctas() ? tiles : (u32)persistent_ctas();
-        ntt_fwd_rows_tma<S1, FORM><<<grid, 256, sizeof(RowsSmem), st>>>(jobs, tiles);
+        const u32 tiles = ngroups * R, ctas = (u32)(resident * sm_count());
+        ntt_fwd_rows_tma<S1, FORM><<<tiles < ctas ? tiles : ctas, 256, sizeof(RowsSmem), st>>>(groups, tiles);
         count_launch();
     }
-    if (njobs > ngrouped) {
-        const u32 rows = (njobs - ngrouped) * R;
-        ntt_fwd_rows<S1, FORM><<<(rows + 15) / 16, 256, 0, st>>>(jobs + ngrouped, rows);
+    if (njobs > 16 * ngroups) {
+        const u32 rows = (njobs - 16 * ngroups) * R;
+        ntt_fwd_rows<S1, FORM><<<(rows + 15) / 16, 256, 0, st>>>(jobs + 16 * ngroups, rows);
         count_launch();
     }
     return cudaGetLastError();
 }
 
 template <int S1, int FORM>
-static cudaError_t inv_impl(const NttJob *jobs, u32 njobs, u32, cudaStream_t st) {
+static cudaError_t inv_impl(const NttJob *jobs, u32 njobs, const NttRowGroup *, u32, cudaStream_t st) {
     constexpr int R = 1 << S1;
     const u32 rows = njobs * R;
     ntt_inv_rows<S1, FORM><<<(rows + 15) / 16, 256, 0, st>>>(jobs, rows);
@@ -596,23 +629,25 @@ static cudaError_t inv_impl(const NttJob *jobs, u32 njobs, u32, cudaStream_t st)
 #define ALOHA_NTT_DISPATCH(IMPL)                                                          \
     if (form > FORM_PM) return cudaErrorInvalidValue;                                     \
     switch (logn * 2 + form) {                                                            \
-    case 16: return IMPL<0, FORM_GENERIC>(jobs, njobs, ngrouped, st); case 17: return IMPL<0, FORM_PM>(jobs, njobs, ngrouped, st); \
-    case 18: return IMPL<1, FORM_GENERIC>(jobs, njobs, ngrouped, st); case 19: return IMPL<1, FORM_PM>(jobs, njobs, ngrouped, st); \
-    case 20: return IMPL<2, FORM_GENERIC>(jobs, njobs, ngrouped, st); case 21: return IMPL<2, FORM_PM>(jobs, njobs, ngrouped, st); \
-    case 22: return IMPL<3, FORM_GENERIC>(jobs, njobs, ngrouped, st); case 23: return IMPL<3, FORM_PM>(jobs, njobs, ngrouped, st); \
-    case 24: return IMPL<4, FORM_GENERIC>(jobs, njobs, ngrouped, st); case 25: return IMPL<4, FORM_PM>(jobs, njobs, ngrouped, st); \
-    case 26: return IMPL<5, FORM_GENERIC>(jobs, njobs, ngrouped, st); case 27: return IMPL<5, FORM_PM>(jobs, njobs, ngrouped, st); \
-    case 28: return IMPL<6, FORM_GENERIC>(jobs, njobs, ngrouped, st); case 29: return IMPL<6, FORM_PM>(jobs, njobs, ngrouped, st); \
-    case 30: return IMPL<7, FORM_GENERIC>(jobs, njobs, ngrouped, st); case 31: return IMPL<7, FORM_PM>(jobs, njobs, ngrouped, st); \
-    case 32: return IMPL<8, FORM_GENERIC>(jobs, njobs, ngrouped, st); case 33: return IMPL<8, FORM_PM>(jobs, njobs, ngrouped, st); \
+    case 16: return IMPL<0, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 17: return IMPL<0, FORM_PM>(jobs, njobs, groups, ngroups, st); \
+    case 18: return IMPL<1, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 19: return IMPL<1, FORM_PM>(jobs, njobs, groups, ngroups, st); \
+    case 20: return IMPL<2, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 21: return IMPL<2, FORM_PM>(jobs, njobs, groups, ngroups, st); \
+    case 22: return IMPL<3, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 23: return IMPL<3, FORM_PM>(jobs, njobs, groups, ngroups, st); \
+    case 24: return IMPL<4, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 25: return IMPL<4, FORM_PM>(jobs, njobs, groups, ngroups, st); \
+    case 26: return IMPL<5, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 27: return IMPL<5, FORM_PM>(jobs, njobs, groups, ngroups, st); \
+    case 28: return IMPL<6, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 29: return IMPL<6, FORM_PM>(jobs, njobs, groups, ngroups, st); \
+    case 30: return IMPL<7, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 31: return IMPL<7, FORM_PM>(jobs, njobs, groups, ngroups, st); \
+    case 32: return IMPL<8, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 33: return IMPL<8, FORM_PM>(jobs, njobs, groups, ngroups, st); \
     default: return cudaErrorInvalidValue;                                                \
     }
-cudaError_t launch_ntt_forward(const NttJob *jobs, u32 njobs, u32 ngrouped, u32 logn, u32 form, cudaStream_t st) {
-    if (ngrouped % 16 || ngrouped > njobs) return cudaErrorInvalidValue;
+cudaError_t launch_ntt_forward(const NttJob *jobs, u32 njobs, const NttRowGroup *groups, u32 ngroups, u32 logn, u32 form,
+                               cudaStream_t st) {
+    if (16 * ngroups > njobs) return cudaErrorInvalidValue;
     ALOHA_NTT_DISPATCH(fwd_impl)
 }
 cudaError_t launch_ntt_inverse(const NttJob *jobs, u32 njobs, u32 logn, u32 form, cudaStream_t st) {
-    const u32 ngrouped = 0;
+    const NttRowGroup *groups = nullptr;
+    const u32 ngroups = 0;
     ALOHA_NTT_DISPATCH(inv_impl)
 }
 

@@ -22,8 +22,22 @@ __device__ __forceinline__ void ct_bf_pm(u64 &x, u64 &y, const Tw &t, u32 d2, u6
     x = x + m;
 }
 
+__device__ __forceinline__ void ct_bf_pm2(u64 &x, u64 &y, const Tw &t, u32 d2, u64 q3) {
+    u64 P, L;
+    mul_pm_parts(y, t.w, t.wp, d2, P, L);
+    y = (x + q3 - P) - L;
+    x = x + P + L;
+}
+__device__ __forceinline__ void ct_bf_pm3(u64 &x, u64 &y, const Tw &t, u32 d2, u64 q3) {
+    u64 P, L;
+    mul_pm_parts(y, t.w, t.wp, d2, P, L);
+    const u64 xn = x + P + L;
+    y = (x + x + q3) - xn;
+    x = xn;
+}
+
 template <int LOGE, int MINB, int PM = 0>
-__global__ void __launch_bounds__(256, MINB) k(u64 *io, const Tw *tw, u64 q, int iters) {
+__global__ void __launch_bounds__(256, MINB) k(u64 *io, const Tw *tw, u64 q, u64 q3, int iters) {
     constexpr int E = 1 << LOGE;
     __shared__ Tw stw[256];
     u64 x[E];
@@ -41,7 +55,9 @@ __global__ void __launch_bounds__(256, MINB) k(u64 *io, const Tw *tw, u64 q, int
             for (int e = 0; e < E; ++e) {
                 if (e & half) continue;
                 if ((e & (half - 1)) == 0) w = stw[(((threadIdx.x >> 5) + it) & 15) * 16 + (1 << v) + (e >> (LOGE - v))];   // warp-uniform: a broadcast, no bank conflicts
-                if (PM) ct_bf_pm(x[e], x[e + half], w, (u32)(2 * nq), 3 * q);   // nq = 2^64 - q = 16 d ... only timing matters here
+                if (PM == 2) ct_bf_pm2(x[e], x[e + half], w, (u32)(2 * nq), q3);
+                else if (PM == 3) ct_bf_pm3(x[e], x[e + half], w, (u32)(2 * nq), q3);
+                else if (PM) ct_bf_pm(x[e], x[e + half], w, (u32)(2 * nq), q3);   // nq = 2^64 - q = 16 d ... only timing matters here
                 else ct_bf(x[e], x[e + half], w, nq, q2);
             }
         }
@@ -66,12 +82,12 @@ void run(int sms, int clk_khz, u64 *io, Tw *tw, u64 q) {
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k<LOGE, MINB, PM>, 256, 0);
     const int blocks = sms * occ;
-    k<LOGE, MINB, PM><<<blocks, 256>>>(io, tw, q, iters);
+    k<LOGE, MINB, PM><<<blocks, 256>>>(io, tw, q, 3 * q, iters);
     cudaDeviceSynchronize();
-    cudaEventRecord(e0); k<LOGE, MINB, PM><<<blocks, 256>>>(io, tw, q, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventRecord(e0); k<LOGE, MINB, PM><<<blocks, 256>>>(io, tw, q, 3 * q, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     const double bf = (double)blocks * 256 * (E / 2 * LOGE) * iters;
-    printf("%s E=%2d minb=%d regs=%3d occ=%d CTA/SM (%2d warps): %.2f bf/clk/SM -> %.2f M limb-NTT/s ceiling\n", PM ? "pseudo-Mersenne" : "Shoup          ", E, MINB,
+    printf("%s E=%2d minb=%d regs=%3d occ=%d CTA/SM (%2d warps): %.2f bf/clk/SM -> %.2f M limb-NTT/s ceiling\n", PM == 1 ? "pseudo-Mersenne" : PM == 2 ? "PM 3-input adds" : PM == 3 ? "PM x'=x+P+L,2x-" : "Shoup          ", E, MINB,
            fa.numRegs, occ, occ * 8, bf / (ms * 1e-3) / (clk_khz * 1e3) / sms, bf / (ms * 1e-3) / 524288 / 1e6);
 }
 
@@ -94,6 +110,10 @@ int main() {
     run<4, 1, 1>(sms, clk_khz, io, tw, q);
     run<4, 2, 1>(sms, clk_khz, io, tw, q);
     run<4, 3, 1>(sms, clk_khz, io, tw, q);
+    run<4, 2, 2>(sms, clk_khz, io, tw, q);
+    run<4, 3, 2>(sms, clk_khz, io, tw, q);
+    run<4, 2, 3>(sms, clk_khz, io, tw, q);
+    run<4, 3, 3>(sms, clk_khz, io, tw, q);
     run<4, 4, 1>(sms, clk_khz, io, tw, q);
     run<3, 4, 1>(sms, clk_khz, io, tw, q);
     run<3, 2>(sms, clk_khz, io, tw, q);
