@@ -39,10 +39,13 @@
 #define COLS_MINB 3
 #endif
 #ifndef ROWS_TMA_MINB
-#define ROWS_TMA_MINB 2
+#define ROWS_TMA_MINB 4      /* CTAs of 16 * ROWS_TMA_TILE threads per SM */
 #endif
 #ifndef ROWS_TMA_STAGES
-#define ROWS_TMA_STAGES 3
+#define ROWS_TMA_STAGES 2
+#endif
+#ifndef ROWS_TMA_TILE
+#define ROWS_TMA_TILE 8      /* rows (= half-warps) per tile and CTA: 8 or 16 */
 #endif
 
 namespace alb {
@@ -274,10 +277,13 @@ __global__ void __launch_bounds__(256, ROWS_MINB) ntt_fwd_rows(const NttJob *__r
 // barrier: a warp that is done with a stage's shared memory counts itself out, and the last one out
 // refills the stage.  The twiddles of a tile are read from shared memory by all 16 half-warps instead of
 // 16 times from L1/L2, and the mid-transform exchange happens in place in the half-warp's own staged row
-// (XOR-swizzled 16-byte chunks instead of padding): 36.3 KiB per stage, two CTAs per SM.
+// slot (padded to 288 words): 40.3 KiB per stage, two stages, two CTAs per SM.  (Three stages, three
+// CTAs per SM at 80 registers, and an XOR-swizzled 2 KiB slot were all measured: no faster.)
 constexpr int kStages = ROWS_TMA_STAGES;
+constexpr int kTileRows = ROWS_TMA_TILE;          // a group of 16 polynomials is 16 / kTileRows tiles per row index
+constexpr int kTilesPerGroupRow = 16 / kTileRows;
 struct RowsSmem {
-    u64 data[kStages][16][256];
+    u64 data[kStages][kTileRows][kRowPad];   // a staged row is 256 words; the exchange uses the padded 288
     Tw tw[kStages][256];
     NttRowGroup grp[kStages];
     u64 full[kStages];
@@ -315,10 +321,10 @@ __device__ __forceinline__ Tw ldtw_s(const Tw *p) {
 #undef ALOHA_LDTW
 #define ALOHA_LDTW ldtw_s
 template <int S1, int FORM>
-__global__ void __launch_bounds__(256, ROWS_TMA_MINB) ntt_fwd_rows_tma(const NttRowGroup *__restrict__ groups, u32 ntiles) {
+__global__ void __launch_bounds__(16 * kTileRows, ROWS_TMA_MINB) ntt_fwd_rows_tma(const NttRowGroup *__restrict__ groups, u32 ntiles) {
     typedef Arith<FORM> AR;
     constexpr int R = 1 << S1;
-    constexpr u32 kStageBytes = 16 * 2048 + 256 * sizeof(Tw) + sizeof(NttRowGroup);
+    constexpr u32 kStageBytes = kTileRows * 2048 + 256 * sizeof(Tw) + sizeof(NttRowGroup);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RowsSmem &S = *reinterpret_cast<RowsSmem *>(smem_raw);
     const int t = threadIdx.x, lane = t & 31, hw = t >> 4, h = t & 15;
@@ -331,12 +337,14 @@ __global__ void __launch_bounds__(256, ROWS_TMA_MINB) ntt_fwd_rows_tma(const Ntt
     }
     __syncthreads();
     // one whole warp: arm stage b and start the copies of `tile` into it
+    // tile -> (group, row index r, which kTileRows of the group's 16 polynomials)
     auto stage_in = [&](u32 tile, int b) {
-        const NttRowGroup *G = groups + tile / R;
-        const size_t off = (size_t)(tile % R) * 256;
+        const u32 sub = tile % kTilesPerGroupRow, gr = tile / kTilesPerGroupRow;
+        const NttRowGroup *G = groups + gr / R;
+        const size_t off = (size_t)(gr % R) * 256;
         if (lane == 0) mbar_arrive_expect_tx(&S.full[b], kStageBytes);
         __syncwarp();
-        if (lane < 16) bulk_g2s(&S.data[b][lane][0], G->src[lane] + off, 2048, &S.full[b]);
+        if (lane < kTileRows) bulk_g2s(&S.data[b][lane][0], G->src[sub * kTileRows + lane] + off, 2048, &S.full[b]);
         else if (lane == 16) bulk_g2s(&S.tw[b][0], G->rtw + off, 256 * sizeof(Tw), &S.full[b]);
         else if (lane == 17) bulk_g2s(&S.grp[b], G, sizeof(NttRowGroup), &S.full[b]);
     };
@@ -347,10 +355,13 @@ __global__ void __launch_bounds__(256, ROWS_TMA_MINB) ntt_fwd_rows_tma(const Ntt
             if (tile + b * stride < ntiles) stage_in(tile + b * stride, b);
     }
     for (u32 i = 0, b = 0, parity = 0; tile < ntiles; ++i, tile += stride) {
+#ifdef ROWS_TMA_NOWAIT   /* timing experiment only: results are garbage */
+        if (i < kStages)
+#endif
         mbar_wait(&S.full[b], parity);
         const NttRowGroup &G = S.grp[b];
         const AR A(G.mc);
-        u64 *dst = G.dst[hw] + (size_t)(tile % R) * 256;
+        u64 *dst = G.dst[(tile % kTilesPerGroupRow) * kTileRows + hw] + (size_t)(tile / kTilesPerGroupRow % R) * 256;
         const Tw *tw = S.tw[b];
         u64 *row = &S.data[b][hw][0];
 
@@ -366,14 +377,14 @@ __global__ void __launch_bounds__(256, ROWS_TMA_MINB) ntt_fwd_rows_tma(const Ntt
         // phase A: level u pairs k-bit (3-u); twiddle j = k >> (4 - u), warp-uniform
 #pragma unroll
         for (int u = 0; u < 4; ++u) ALOHA_CT_STAGE(16, 8 >> u, row_slot(u, g0 >> (4 - u)))
-        // exchange h + 16 k -> 16 h + e.  Word (k, h) lives in 128-byte line k, 16-byte chunk (h/2) ^ (k mod 8):
-        // the 16 lanes write one whole line, and the 8 lanes of an LDS.128 phase read 8 different chunks.
+        // exchange h + 16 k -> 16 h + e, in place in the half-warp's own staged row
+        // word jj at jj + 2 (jj >> 4): strided writes and 16-byte reads both conflict-free, all offsets immediates
 #pragma unroll
-        for (int k = 0; k < 16; ++k) row[16 * k + ((((h >> 1) ^ (k & 7)) << 1) | (h & 1))] = x[k];
+        for (int k = 0; k < 16; ++k) row[h + 18 * k] = x[k];
         __syncwarp();
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
-            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(row + 16 * h + (((e >> 1) ^ (h & 7)) << 1));
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(row + 18 * h + e);
             x[e] = v.x;
             x[e + 1] = v.y;
         }
@@ -388,13 +399,11 @@ __global__ void __launch_bounds__(256, ROWS_TMA_MINB) ntt_fwd_rows_tma(const Ntt
         __syncwarp();
         u32 last = 0;
         if (lane == 0) {
-            last = atomicAdd(&S.done[b], 1u) == 7u;
+            last = atomicAdd(&S.done[b], 1u) == kTileRows / 2 - 1;   // kTileRows / 2 warps share the stage
             if (last) S.done[b] = 0;
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last && tile + kStages * stride < ntiles) stage_in(tile + kStages * stride, b);
-        // all eight 16-byte values first, then the stores: distinct register quads, so no store waits for
-        // the previous one to release its source registers
         // 16-byte stores whose four words are selected straight into the store's register quad
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
@@ -432,7 +441,7 @@ __global__ void __launch_bounds__(256, ROWS_TMA_MINB) ntt_fwd_rows_tma(const Ntt
             if (e & (HALF)) continue;                                                               \
             if ((e & ((HALF)-1)) == 0) {                                                            \
                 const int g0 = e & ~(2 * (HALF)-1);                                                 \
-                w_ = ldtw(tw + (TWIDX));                                                            \
+                w_ = ALOHA_LDTW(tw + (TWIDX));                                                      \
             }                                                                                       \
             ALOHA_GS_REDUCE_PAIR(e, e + (HALF))                                                     \
             const u64 d_ = x[e] - x[e + (HALF)] + A.off(by_);                                       \
@@ -592,12 +601,12 @@ static cudaError_t fwd_impl(const NttJob *jobs, u32 njobs, const NttRowGroup *gr
         static int resident = 0;            // CTAs of the persistent row pass that fit on one SM
         if (!resident) {
             cudaError_t e = cudaFuncSetAttribute(ntt_fwd_rows_tma<S1, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmem));
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ntt_fwd_rows_tma<S1, FORM>, 256, sizeof(RowsSmem));
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ntt_fwd_rows_tma<S1, FORM>, 16 * kTileRows, sizeof(RowsSmem));
             if (e != cudaSuccess) return e;
             if (resident < 1) return cudaErrorLaunchOutOfResources;
         }
-        const u32 tiles = ngroups * R, ctas = (u32)(resident * sm_count());
-        ntt_fwd_rows_tma<S1, FORM><<<tiles < ctas ? tiles : ctas, 256, sizeof(RowsSmem), st>>>(groups, tiles);
+        const u32 tiles = ngroups * R * kTilesPerGroupRow, ctas = (u32)(resident * sm_count());
+        ntt_fwd_rows_tma<S1, FORM><<<tiles < ctas ? tiles : ctas, 16 * kTileRows, sizeof(RowsSmem), st>>>(groups, tiles);
         count_launch();
     }
     if (njobs > 16 * ngroups) {
@@ -608,6 +617,9 @@ static cudaError_t fwd_impl(const NttJob *jobs, u32 njobs, const NttRowGroup *gr
     return cudaGetLastError();
 }
 
+// The inverse row pass stays un-staged: its threads start from 16 CONTIGUOUS coefficients, which a linear
+// TMA copy can only deliver with 8-way bank conflicts, and staging the row as 16 padded 128-byte copies
+// per row (256 bulk copies per tile) measured 19 % slower than loading straight into registers.
 template <int S1, int FORM>
 static cudaError_t inv_impl(const NttJob *jobs, u32 njobs, const NttRowGroup *, u32, cudaStream_t st) {
     constexpr int R = 1 << S1;

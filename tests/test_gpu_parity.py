@@ -153,6 +153,40 @@ def test_grouped_row_pass_and_modulus_forms(logn, flags):
     assert (back == x % qv).all()
 
 
+@pytest.mark.parametrize("n", [256, 2048])
+@pytest.mark.parametrize("pre", ["vcpy", "vfqmod"])
+def test_grouped_row_pass_with_folded_load_op(n, pre):
+    """Base-extension pattern (VCPY / VFQMOD feeding VNTT) on 20 polynomials per modulus: the element-wise op
+    is folded into the transform's load, and at N = 256 that load sits in the row pass itself -- here the
+    TMA-staged one for 16 of the 20 and the plain one for the other 4.  Raw 64-bit input words."""
+    B = 20
+    rp = n // 128
+    primes = O.synthetic_primes(1, 2 * n) + O.synthetic_primes(1, 2 * n, below=(1 << 60) - (1 << 40))
+    psis = [O.min_primitive_root(q, 2 * n) for q in primes]
+    L = len(primes)
+    rows = B * L * rp
+    prog = asm.Program().vsetvl(n)
+    for l, q in enumerate(primes):
+        prog.vsetq(q).vle(0, 0, l * rp)
+        getattr(prog, pre)(3, 0)
+        prog.vntt(2, 3).vse(2, 2, l * rp)
+    prog.brk()
+    machines = [O.GoldenModel(vlmax_bits=n * 64, spm_rows=2 * rows, ksk_rows=0, moduli=list(zip(primes, psis))),
+                A.Engine(vlmax_bits=n * 64, spm_rows=2 * rows, ksk_rows=0, moduli=list(zip(primes, psis)))]
+    rng = np.random.default_rng(n)
+    # VFQMOD accepts any word; VCPY's two conditional subtracts leave words below 3q under 2q ... keep to < 2q there
+    x = rng.integers(0, 1 << 64, B * L * n, dtype=np.uint64) if pre == "vfqmod" else \
+        rng.integers(0, 2 * min(primes), B * L * n, dtype=np.uint64)
+    out = []
+    for m in machines:
+        m.load_isram(prog.words(), 0)
+        m.dma_mem_h2d(0, x)
+        m.run_vp_batch(0, [(b * L * rp, 0, rows + b * L * rp, 0, 0) for b in range(B)])
+        out.append(m.dma_mem_d2h(rows, B * L * n))
+    assert (out[0] == out[1]).all()
+    assert machines[1].stats()["ops_fused"] >= B          # the last limb's temporary stays live and is not folded
+
+
 ALU_STREAMS = [("vfqmul", None), ("vfqadd", None), ("vfqsub", None), ("vfqmul", 0x123456789abcdef),
                ("vfqadd", (1 << 60) + 5), ("vfqsub", 77)]
 ALU_CODE = {("vfqmul", False): 0x00, ("vfqadd", False): 0x01, ("vfqsub", False): 0x02,
