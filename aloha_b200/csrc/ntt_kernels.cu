@@ -277,8 +277,10 @@ __global__ void __launch_bounds__(256, ROWS_MINB) ntt_fwd_rows(const NttJob *__r
 // barrier: a warp that is done with a stage's shared memory counts itself out, and the last one out
 // refills the stage.  The twiddles of a tile are read from shared memory by all 16 half-warps instead of
 // 16 times from L1/L2, and the mid-transform exchange happens in place in the half-warp's own staged row
-// slot (padded to 288 words): 40.3 KiB per stage, two stages, two CTAs per SM.  (Three stages, three
-// CTAs per SM at 80 registers, and an XOR-swizzled 2 KiB slot were all measured: no faster.)
+// slot (padded to 288 words).  A CTA is kTileRows / 2 warps; with 8-row tiles a stage is 22.3 KiB and
+// four CTAs fit on an SM.  Measured alternatives, none faster: 16-row tiles (4 % slower -- more warps
+// wait on each other's stage), three stages, 80 registers for more CTAs, an XOR-swizzled 2 KiB slot,
+// refilling the rows half a tile earlier than the twiddles.
 constexpr int kStages = ROWS_TMA_STAGES;
 constexpr int kTileRows = ROWS_TMA_TILE;          // a group of 16 polynomials is 16 / kTileRows tiles per row index
 constexpr int kTilesPerGroupRow = 16 / kTileRows;
@@ -355,9 +357,6 @@ __global__ void __launch_bounds__(16 * kTileRows, ROWS_TMA_MINB) ntt_fwd_rows_tm
             if (tile + b * stride < ntiles) stage_in(tile + b * stride, b);
     }
     for (u32 i = 0, b = 0, parity = 0; tile < ntiles; ++i, tile += stride) {
-#ifdef ROWS_TMA_NOWAIT   /* timing experiment only: results are garbage */
-        if (i < kStages)
-#endif
         mbar_wait(&S.full[b], parity);
         const NttRowGroup &G = S.grp[b];
         const AR A(G.mc);

@@ -172,6 +172,8 @@ def workload_config():
     return {"workload": "batched negacyclic NTT, N=65536, 32 RNS limbs x 64 polynomials per GPU "
                         "(BASELINE.json configs[2])",
             "n": N, "limbs": LIMBS, "polys": POLYS, "limb_ntts_per_step_per_gpu": LIMBS * POLYS,
+            "moduli": "the 32 primes below 2^60 with q = 1 mod 2^17, scanning downward (SURVEY 8(d)3): all of the form "
+                      "2^60 - d with d < 2^27, which the engine detects and serves with its pseudo-Mersenne product",
             "l2": "inputs (1 GiB) + outputs (1 GiB) per step exceed L2; no flush needed",
             "warmup_policy": "W steps, then continuous load until 0.4 s have passed (sustained clocks; sw_power_cap may be active)",
             "parallelism": "limb/poly-sharded, no data-path collective"}
@@ -382,10 +384,15 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "traffic_note": "dram__bytes_read+write of the column + row kernels for one step, from one ncu --set full capture (profiles/r1_ntt_traffic.json)",
-                         "co_bound": {"what": "integer issue (IMAD.WIDE ~2.3 and carry-chain ALU ~1.7 issue cycles per warp instruction; tools/bf_parts.cu)",
-                                      "arithmetic_only_ceiling_limb_ntts_per_s": [1.2e6, 1.55e6], "imad_issue_bound_limb_ntts_per_s": 3.1e6,
+                         "co_bound": {"what": "integer issue: the butterflies alone (registers only, no memory; tools/bf_bench.cu) run at "
+                                              "4.09 butterflies/clk/SM with the pseudo-Mersenne product (3.02 with Shoup's), i.e. the "
+                                              "arithmetic caps this two-pass transform at 2.27 M limb-NTTs/s; the board's 600 W software "
+                                              "power cap holds the sustained figure a further 7 % under the burst one",
+                                      "arithmetic_only_ceiling_limb_ntts_per_s": 2.27e6,
+                                      "arithmetic_only_ceiling_generic_primes_limb_ntts_per_s": 1.67e6,
                                       "see": "DESIGN.md section 5"},
-                         "kernel": "ntt_fwd_cols<8> + ntt_fwd_rows<8> (one limb-NTT = one column pass + one row pass)",
+                         "kernel": "ntt_fwd_cols<8,1> + ntt_fwd_rows_tma<8,1> (one limb-NTT = one column pass + one TMA-staged row pass; "
+                                   "<.,1> = pseudo-Mersenne arithmetic, which the workload's prime rule selects)",
                          "algorithmic_bytes_per_limb_ntt": ALG_BYTES_PER_NTT},
             "intt": {"value": inv_value, "unit": "limb-NTTs/s", "ms_per_step": ms_inv / args.steps},
             "engine_stats": {k: s1[k] - s0[k] for k in s1},
