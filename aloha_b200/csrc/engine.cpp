@@ -56,6 +56,51 @@ Tw twiddle(u64 w, u64 q, u32 form) {
     return t;
 }
 
+// Which tensor map covers p, and p's offset inside that buffer in 128-byte lines (kernels.cuh TmaMaps).
+bool tensor_coords(const aloha *E, const u64 *p, u32 *map, u32 *line) {
+    const struct { const u64 *base; u64 words; } bufs[3] = {
+        {E->d_spm, E->spm_words}, {E->d_ksk, E->ksk_words}, {E->d_pool, (u64)E->pool_count * E->nmax}};
+    for (u32 i = 0; i < 3; ++i)
+        if (bufs[i].base && p >= bufs[i].base && p < bufs[i].base + bufs[i].words) {
+            const u64 off = (u64)(p - bufs[i].base);
+            if (off % 16) return false;
+            *map = i;
+            *line = (u32)(off / 16);
+            return true;
+        }
+    return false;
+}
+
+// Swizzled tensor maps over the three buffers.  The encoder lives in the driver; without it (or if it
+// refuses) the inverse transforms simply keep their plain row pass.
+void build_tensor_maps(aloha *E) {
+    typedef CUresult (*Encode)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    const struct { u64 *base; u64 words; } bufs[3] = {
+        {E->d_spm, E->spm_words}, {E->d_ksk, E->ksk_words}, {E->d_pool, (u64)E->pool_count * E->nmax}};
+    for (int i = 0; i < 3; ++i) {
+        u64 *base = bufs[i].base ? bufs[i].base : E->d_spm;            // an absent buffer is never selected
+        const u64 words = bufs[i].base ? bufs[i].words : E->spm_words;
+        const cuuint64_t dims[2] = {16, words / 16};
+        const cuuint64_t strides[1] = {128};
+        const cuuint32_t box[2] = {16, 16}, estr[2] = {1, 1};
+        if (words < 256 || dims[1] > (1ull << 32) ||
+            ((Encode)fn)(&E->tma_maps.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return;
+    }
+    E->tma_maps_ok = true;
+}
+
 // ------------------------------------------------------------------------------ twiddle tables
 // Index j holds root^bitrev(j, logN) -- the reference ROM's order
 // (sim/vp/tf_rom_generator/tf_rom_generator.sv:28-30,61-63,111,147-148).
@@ -82,17 +127,23 @@ int get_tables(aloha *E, int mod, unsigned logn, const TwTable **out) {
     }
     // the forward row pass's view: row r of the N/256 x 256 layout uses tw[((R + r) << u) + j], u < 8
     const u64 R = n / 256;
-    std::vector<Tw> fwd_rows(n, Tw{0, 0});
+    // inverse row pass: GS level lt < 8 of row r uses itw[2^(logN-1-lt) + (r << (7-lt)) + j], j < 2^(7-lt)
+    std::vector<Tw> fwd_rows(n, Tw{0, 0}), inv_rows(n, Tw{0, 0});
     for (u64 r = 0; r < R; ++r)
         for (u32 u = 0; u < 8; ++u)
-            for (u32 j = 0; j < (1u << u); ++j) fwd_rows[r * 256 + row_slot(u, j)] = fwd[((R + r) << u) + j];
+            for (u32 j = 0; j < (1u << u); ++j) {
+                fwd_rows[r * 256 + row_slot(u, j)] = fwd[((R + r) << u) + j];
+                inv_rows[r * 256 + row_slot(u, j)] = inv[(1ull << (logn - 8 + u)) + (r << u) + j];
+            }
     TwTable t;
     CU(cudaMalloc(&t.fwd, n * sizeof(Tw)));
     CU(cudaMalloc(&t.inv, n * sizeof(Tw)));
     CU(cudaMalloc(&t.fwd_rows, n * sizeof(Tw)));
+    CU(cudaMalloc(&t.inv_rows, n * sizeof(Tw)));
     CU(cudaMemcpy(t.fwd, fwd.data(), n * sizeof(Tw), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(t.inv, inv.data(), n * sizeof(Tw), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(t.fwd_rows, fwd_rows.data(), n * sizeof(Tw), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t.inv_rows, inv_rows.data(), n * sizeof(Tw), cudaMemcpyHostToDevice));
     const u64 ninv = powmod(n % q, q - 2, q);
     const Tw a = twiddle(ninv, q, form), b = twiddle((u64)((u128)inv[1].w * ninv % q), q, form);
     t.mc.q = q;
@@ -108,7 +159,7 @@ int get_tables(aloha *E, int mod, unsigned logn, const TwTable **out) {
 }
 
 void free_tables(aloha *E) {
-    for (auto &kv : E->tw_tables) { cudaFree(kv.second.fwd); cudaFree(kv.second.inv); cudaFree(kv.second.fwd_rows); }
+    for (auto &kv : E->tw_tables) { cudaFree(kv.second.fwd); cudaFree(kv.second.inv); cudaFree(kv.second.fwd_rows); cudaFree(kv.second.inv_rows); }
     E->tw_tables.clear();
 }
 void free_plans(aloha *E) {
@@ -694,8 +745,8 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
         for (size_t c = i; c < j;) {
             const size_t cnt = std::min(max_jobs, j - c);
             Launch L{h.kind, h.alu, h.n, (u32)cnt, tables.size()};
-            if (h.kind == K_NTT && cnt >= 16) {
-                // forward transforms: same-modulus runs of 16 first (they take the TMA-staged row pass,
+            if ((h.kind == K_NTT || (h.kind == K_INTT && E->tma_maps_ok)) && cnt >= 16) {
+                // transforms: same-modulus runs of 16 first (they take the TMA-staged row pass,
                 // one tile = one row of 16 polynomials sharing its twiddles), the remainder after them
                 std::map<std::pair<int, u32>, std::vector<size_t>> by_mod;
                 for (size_t t = c; t < c + cnt; ++t) by_mod[{ops[order[t]].mod, ops[order[t]].pre}].push_back(order[t]);
@@ -737,7 +788,7 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
                     const TwTable *tw;
                     int rc = get_tables(E, o.mod, ilog2(o.n), &tw);
                     if (rc) return rc;
-                    NttJob nj{o.a, o.dst, o.kind == K_NTT ? tw->fwd : tw->inv, o.kind == K_NTT ? tw->fwd_rows : nullptr, tw->mc};
+                    NttJob nj{o.a, o.dst, o.kind == K_NTT ? tw->fwd : tw->inv, o.kind == K_NTT ? tw->fwd_rows : tw->inv_rows, tw->mc};
                     nj.mc.pre = o.pre;
                     append(tables, nj);
                     break;
@@ -750,8 +801,10 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
                     NttRowGroup G{};
                     const NttJob *nj = reinterpret_cast<const NttJob *>(tables.data() + L.table_off) + 16 * g;
                     for (int k = 0; k < 16; ++k) {
-                        G.src[k] = h.n == 256 ? nj[k].src : nj[k].dst;
+                        G.src[k] = (h.kind == K_INTT || h.n == 256) ? nj[k].src : nj[k].dst;
                         G.dst[k] = nj[k].dst;
+                        if (h.kind == K_INTT && !tensor_coords(E, G.src[k], &G.src_map[k], &G.src_line[k]))
+                            return fail(E, ALOHA_E_STATE, "transform source outside the device buffers");
                     }
                     G.rtw = nj[0].rtw;
                     G.mc = nj[0].mc;
@@ -810,7 +863,7 @@ int issue(aloha *E, const Plan &plan, u64 *launched) {
         case K_VAUT: e = launch_vaut((const PermJob *)tab, L.njobs, L.n, E->stream); break;
         case K_VROLI: e = launch_vroli((const PermJob *)tab, L.njobs, L.n, E->stream); break;
         case K_NTT: e = launch_ntt_forward((const NttJob *)tab, L.njobs, (const NttRowGroup *)(base + L.group_off), L.ngroups, ilog2(L.n), L.alu, E->stream); break;
-        case K_INTT: e = launch_ntt_inverse((const NttJob *)tab, L.njobs, ilog2(L.n), L.alu, E->stream); break;
+        case K_INTT: e = launch_ntt_inverse((const NttJob *)tab, L.njobs, (const NttRowGroup *)(base + L.group_off), L.ngroups, &E->tma_maps, ilog2(L.n), L.alu, E->stream); break;
         }
         if (e != cudaSuccess) {
             E->last_error = std::string("kernel launch: ") + cudaGetErrorString(e);
@@ -1072,6 +1125,7 @@ int aloha_create(const aloha_cfg *cfg, aloha_t **out) {
         CU(cudaMemsetAsync(E->d_ksk, 0, E->ksk_words * 8, E->stream));
     }
     CU(cudaMalloc(&E->d_pool, (u64)E->pool_count * nmax * 8));
+    build_tensor_maps(E);
     E->iram_depth = cfg->isram_depth ? cfg->isram_depth : kIramDepthDefault;
     E->isram.assign(E->iram_depth * 12, 0);
     E->written.assign((E->spm_words + 7) / 8, 0);

@@ -66,7 +66,7 @@ struct Launch {
 
 struct TwTable {
     Tw *fwd = nullptr, *inv = nullptr;
-    Tw *fwd_rows = nullptr;   // forward twiddles in the row pass's read order (kernels.cuh row_slot)
+    Tw *fwd_rows = nullptr, *inv_rows = nullptr;   // the same twiddles in the row passes' read order (kernels.cuh row_slot)
     ModulusConsts mc{};
 };
 
@@ -105,6 +105,8 @@ struct aloha {
     std::vector<uint32_t> queued_pcs;                          // ALOHA_F_DEFER: run_vp calls not yet planned
     std::vector<aloha_vp_args> queued_args;
     alb::u64 *d_spm = nullptr, *d_ksk = nullptr, *d_pool = nullptr;
+    alb::TmaMaps tma_maps{};      // swizzled tensor maps over d_spm / d_ksk / d_pool (inverse row pass)
+    bool tma_maps_ok = false;
     alb::u64 spm_words = 0, ksk_words = 0;
     uint32_t pool_count = 0;
     alb::u64 iram_depth = alb::kIramDepthDefault;

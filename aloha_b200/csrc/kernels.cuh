@@ -3,6 +3,7 @@
 // single launch serves a whole batch of independent limb-polynomials (different moduli, different
 // SPM / vreg / KSK addresses).
 #pragma once
+#include <cuda.h>            // CUtensorMap (type only; the encoder is fetched from the driver at run time)
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -122,15 +123,27 @@ struct AutMacJob {
     u64 q, iq, k, kinv;
 };
 
-// 16 forward jobs that share a modulus (and load op), as the TMA-staged row pass wants them: one record
-// is one bulk copy.  `src` is what the row pass reads: the column pass's output (= dst), or the job's
-// source when N = 256 and there is no column pass.
+// 16 jobs of one direction that share a modulus (and load op), as the TMA-staged row passes want them:
+// one record is one bulk copy.  `src` is what the row pass reads -- forward: the column pass's output
+// (= dst), or the job's source when N = 256 and there is no column pass; inverse: the job's source, which
+// the inverse pass fetches through a tensor map (`src_map` = which device buffer, `src_line` = offset of
+// the polynomial inside it in 128-byte lines).
 struct __align__(16) NttRowGroup {
     const u64 *src[16];
     u64 *dst[16];
     const Tw *rtw;
     u64 pad;
     ModulusConsts mc;
+    u32 src_line[16];
+    u32 src_map[16];
+};
+
+// Tensor maps over the device buffers a transform can read (SPM image, KSK image, renaming pool), each seen
+// as [lines][16 words] with SWIZZLE_128B: a 16 x 16 box is one 2 KiB row of a polynomial, landing in shared
+// memory with 16-byte chunk c of line l at chunk c ^ (l mod 8) -- the layout in which a thread can read
+// its 16 contiguous coefficients without bank conflicts.
+struct TmaMaps {
+    CUtensorMap m[3];
 };
 
 // every job of one launch has mc.form == form.  The first 16 * ngroups jobs are also described by
@@ -138,7 +151,8 @@ struct __align__(16) NttRowGroup {
 // kernel, one tile = the same row of 16 polynomials, twiddles staged once per tile.
 cudaError_t launch_ntt_forward(const NttJob *jobs_dev, u32 njobs, const NttRowGroup *groups_dev, u32 ngroups, u32 logn,
                                u32 form, cudaStream_t st);
-cudaError_t launch_ntt_inverse(const NttJob *jobs_dev, u32 njobs, u32 logn, u32 form, cudaStream_t st);
+cudaError_t launch_ntt_inverse(const NttJob *jobs_dev, u32 njobs, const NttRowGroup *groups_dev, u32 ngroups,
+                               const TmaMaps *maps_host, u32 logn, u32 form, cudaStream_t st);
 cudaError_t launch_ew(u32 alu_op, const EwJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
 cudaError_t launch_vaut(const PermJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
 cudaError_t launch_vroli(const PermJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);

@@ -520,6 +520,129 @@ __global__ void __launch_bounds__(256, ROWS_MINB) ntt_inv_rows(const NttJob *__r
     for (int k = 0; k < 16; ++k) dst[h + 16 * k] = x[k];  // < 2q (canonical when S1 == 0)
 }
 
+// ============================================================================ inverse: rows, TMA-staged
+// The mirror image of ntt_fwd_rows_tma.  A thread starts from 16 CONTIGUOUS coefficients (line h of the
+// row), which a linear copy would deliver with 8-way bank conflicts, so the rows come in through a
+// tensor map with SWIZZLE_128B (kernels.cuh TmaMaps): chunk c of line l sits at chunk c ^ (l mod 8), the 8
+// lanes of an LDS.128 phase read 8 different chunks, and the exchange runs in place in the same layout.
+// Twiddles: the row's 255 inverse twiddles, level lt stored at row_slot(7 - lt, .).
+struct InvRowsSmem {
+    u64 data[kStages][kTileRows][256];     // first member: the swizzle pattern wants 1 KiB alignment
+    Tw tw[kStages][256];
+    NttRowGroup grp[kStages];
+    u64 full[kStages];
+    u32 done[kStages];
+};
+static_assert(sizeof(InvRowsSmem) + 1024 <= (233472 - ROWS_TMA_MINB * 1024) / ROWS_TMA_MINB, "ROWS_TMA_MINB CTAs per SM");
+
+__device__ __forceinline__ void tensor_g2s_2d(void *dst, const CUtensorMap *map, u32 c0, u32 c1, u64 *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_addr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_addr(bar)) : "memory");
+}
+
+#undef ALOHA_LDTW
+#define ALOHA_LDTW ldtw_s
+template <int S1, int FORM>
+__global__ void __launch_bounds__(16 * kTileRows, ROWS_TMA_MINB)
+ntt_inv_rows_tma(const NttRowGroup *__restrict__ groups, u32 ntiles, const __grid_constant__ TmaMaps maps) {
+    typedef Arith<FORM> AR;
+    constexpr int R = 1 << S1;
+    constexpr u32 kStageBytes = kTileRows * 2048 + 256 * sizeof(Tw) + sizeof(NttRowGroup);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // the swizzle pattern is a function of the shared-memory address: round the window up to 1 KiB (the
+    // launch allocates 1 KiB of slack)
+    InvRowsSmem &S = *reinterpret_cast<InvRowsSmem *>(smem_raw + ((1024 - (smem_addr(smem_raw) & 1023)) & 1023));
+    const int t = threadIdx.x, lane = t & 31, hw = t >> 4, h = t & 15;
+    if (t == 0) {
+        for (int b = 0; b < kStages; ++b) {
+            mbar_init(&S.full[b], 1);
+            S.done[b] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto stage_in = [&](u32 tile, int b) {
+        const u32 sub = tile % kTilesPerGroupRow, gr = tile / kTilesPerGroupRow;
+        const NttRowGroup *G = groups + gr / R;
+        const u32 r = gr % R;
+        if (lane == 0) mbar_arrive_expect_tx(&S.full[b], kStageBytes);
+        __syncwarp();
+        if (lane < kTileRows) {
+            const int k = sub * kTileRows + lane;
+            tensor_g2s_2d(&S.data[b][lane][0], &maps.m[G->src_map[k]], 0, G->src_line[k] + 16 * r, &S.full[b]);
+        } else if (lane == 16) {
+            bulk_g2s(&S.tw[b][0], G->rtw + (size_t)r * 256, 256 * sizeof(Tw), &S.full[b]);
+        } else if (lane == 17) {
+            bulk_g2s(&S.grp[b], G, sizeof(NttRowGroup), &S.full[b]);
+        }
+    };
+    const u32 stride = gridDim.x;
+    u32 tile = blockIdx.x;
+    if (t < 32) {
+        for (int b = 0; b < kStages; ++b)
+            if (tile + b * stride < ntiles) stage_in(tile + b * stride, b);
+    }
+    for (u32 i = 0, b = 0, parity = 0; tile < ntiles; ++i, tile += stride) {
+        mbar_wait(&S.full[b], parity);
+        const NttRowGroup &job = S.grp[b];
+        const AR A(job.mc);
+        u64 *dst = job.dst[(tile % kTilesPerGroupRow) * kTileRows + hw] + (size_t)(tile / kTilesPerGroupRow % R) * 256;
+        const Tw *tw = S.tw[b];
+        u64 *row = &S.data[b][hw][0];
+        u64 *mine = row + 16 * h;          // line h: this thread's 16 contiguous coefficients, chunks XOR (h mod 8)
+
+        u64 x[16];
+        int bnd[16];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(mine + (((e >> 1) ^ (h & 7)) << 1));
+            x[e] = v.x;          // < 2q (see header)
+            x[e + 1] = v.y;
+            bnd[e] = bnd[e + 1] = 2;
+        }
+        // lt = 0..3 pair e-bit lt; twiddle j = (16 h + e) >> (lt + 1) of level lt
+#pragma unroll
+        for (int lt = 0; lt < 4; ++lt) ALOHA_GS_STAGE(16, 1 << lt, row_slot(7 - lt, (16 * h + g0) >> (lt + 1)))
+        ALOHA_GS_NORMALISE(16)
+        // exchange 16 h + e -> h + 16 k, in place: a thread overwrites exactly the words it read
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+            ulonglong2 v;
+            v.x = x[e];
+            v.y = x[e + 1];
+            *reinterpret_cast<ulonglong2 *>(mine + (((e >> 1) ^ (h & 7)) << 1)) = v;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = row[16 * k + ((((h >> 1) ^ (k & 7)) << 1) | (h & 1))];
+        // lt = 4..7 pair k-bit (lt-4); twiddle j = k >> (lt - 3)
+#pragma unroll
+        for (int lt = 4; lt < 8; ++lt) {
+            if (S1 == 0 && lt == 7) {
+                ALOHA_GS_LAST(16)
+            } else {
+                ALOHA_GS_STAGE(16, 1 << (lt - 4), row_slot(7 - lt, g0 >> (lt - 3)))
+            }
+        }
+        if (S1 != 0) ALOHA_GS_NORMALISE(16)
+        // leave the stage (see ntt_fwd_rows_tma), then store
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        u32 last = 0;
+        if (lane == 0) {
+            last = atomicAdd(&S.done[b], 1u) == kTileRows / 2 - 1;
+            if (last) S.done[b] = 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && tile + kStages * stride < ntiles) stage_in(tile + kStages * stride, b);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) asm volatile("st.global.u64 [%0], %1;" ::"l"(dst + h + 16 * k), "l"(x[k]) : "memory");
+        if (++b == kStages) { b = 0; parity ^= 1; }
+    }
+}
+#undef ALOHA_LDTW
+#define ALOHA_LDTW ldtw
+
 // ============================================================================ inverse: columns
 // GS stages lt = 8 .. 8+S1-1, row-distance bit b = lt - 8.  m = 2^(S1-1-b), idx = m + (r >> (b+1)).
 template <int S1, int FORM>
@@ -616,15 +739,28 @@ static cudaError_t fwd_impl(const NttJob *jobs, u32 njobs, const NttRowGroup *gr
     return cudaGetLastError();
 }
 
-// The inverse row pass stays un-staged: its threads start from 16 CONTIGUOUS coefficients, which a linear
-// TMA copy can only deliver with 8-way bank conflicts, and staging the row as 16 padded 128-byte copies
-// per row (256 bulk copies per tile) measured 19 % slower than loading straight into registers.
 template <int S1, int FORM>
-static cudaError_t inv_impl(const NttJob *jobs, u32 njobs, const NttRowGroup *, u32, cudaStream_t st) {
+static cudaError_t inv_impl(const NttJob *jobs, u32 njobs, const NttRowGroup *groups, u32 ngroups, const TmaMaps *maps,
+                            cudaStream_t st) {
     constexpr int R = 1 << S1;
-    const u32 rows = njobs * R;
-    ntt_inv_rows<S1, FORM><<<(rows + 15) / 16, 256, 0, st>>>(jobs, rows);
-    count_launch();
+    if (ngroups) {
+        constexpr size_t kSmem = sizeof(InvRowsSmem) + 1024;
+        static int resident = 0;
+        if (!resident) {
+            cudaError_t e = cudaFuncSetAttribute(ntt_inv_rows_tma<S1, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ntt_inv_rows_tma<S1, FORM>, 16 * kTileRows, kSmem);
+            if (e != cudaSuccess) return e;
+            if (resident < 1) return cudaErrorLaunchOutOfResources;
+        }
+        const u32 tiles = ngroups * R * kTilesPerGroupRow, ctas = (u32)(resident * sm_count());
+        ntt_inv_rows_tma<S1, FORM><<<tiles < ctas ? tiles : ctas, 16 * kTileRows, kSmem, st>>>(groups, tiles, *maps);
+        count_launch();
+    }
+    if (njobs > 16 * ngroups) {
+        const u32 rows = (njobs - 16 * ngroups) * R;
+        ntt_inv_rows<S1, FORM><<<(rows + 15) / 16, 256, 0, st>>>(jobs + 16 * ngroups, rows);
+        count_launch();
+    }
     if constexpr (S1 > 0) {
         constexpr int LA = S1 < 4 ? S1 : 4, H = R >> LA;
         const size_t smem = S1 > 4 ? (size_t)4096 * 8 : 0;
@@ -637,29 +773,29 @@ static cudaError_t inv_impl(const NttJob *jobs, u32 njobs, const NttRowGroup *, 
 // A forward job runs columns src->dst then rows dst->dst; an inverse job rows src->dst then columns
 // dst->dst.  src == dst (exactly) is allowed: every CTA / half-warp reads its whole tile before it
 // writes it.  Partially overlapping src / dst is the caller's bug.
-#define ALOHA_NTT_DISPATCH(IMPL)                                                          \
+#define ALOHA_NTT_DISPATCH(IMPL, ...)                                                          \
     if (form > FORM_PM) return cudaErrorInvalidValue;                                     \
     switch (logn * 2 + form) {                                                            \
-    case 16: return IMPL<0, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 17: return IMPL<0, FORM_PM>(jobs, njobs, groups, ngroups, st); \
-    case 18: return IMPL<1, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 19: return IMPL<1, FORM_PM>(jobs, njobs, groups, ngroups, st); \
-    case 20: return IMPL<2, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 21: return IMPL<2, FORM_PM>(jobs, njobs, groups, ngroups, st); \
-    case 22: return IMPL<3, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 23: return IMPL<3, FORM_PM>(jobs, njobs, groups, ngroups, st); \
-    case 24: return IMPL<4, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 25: return IMPL<4, FORM_PM>(jobs, njobs, groups, ngroups, st); \
-    case 26: return IMPL<5, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 27: return IMPL<5, FORM_PM>(jobs, njobs, groups, ngroups, st); \
-    case 28: return IMPL<6, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 29: return IMPL<6, FORM_PM>(jobs, njobs, groups, ngroups, st); \
-    case 30: return IMPL<7, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 31: return IMPL<7, FORM_PM>(jobs, njobs, groups, ngroups, st); \
-    case 32: return IMPL<8, FORM_GENERIC>(jobs, njobs, groups, ngroups, st); case 33: return IMPL<8, FORM_PM>(jobs, njobs, groups, ngroups, st); \
+    case 16: return IMPL<0, FORM_GENERIC>(jobs, njobs, groups, ngroups, __VA_ARGS__); case 17: return IMPL<0, FORM_PM>(jobs, njobs, groups, ngroups, __VA_ARGS__); \
+    case 18: return IMPL<1, FORM_GENERIC>(jobs, njobs, groups, ngroups, __VA_ARGS__); case 19: return IMPL<1, FORM_PM>(jobs, njobs, groups, ngroups, __VA_ARGS__); \
+    case 20: return IMPL<2, FORM_GENERIC>(jobs, njobs, groups, ngroups, __VA_ARGS__); case 21: return IMPL<2, FORM_PM>(jobs, njobs, groups, ngroups, __VA_ARGS__); \
+    case 22: return IMPL<3, FORM_GENERIC>(jobs, njobs, groups, ngroups, __VA_ARGS__); case 23: return IMPL<3, FORM_PM>(jobs, njobs, groups, ngroups, __VA_ARGS__); \
+    case 24: return IMPL<4, FORM_GENERIC>(jobs, njobs, groups, ngroups, __VA_ARGS__); case 25: return IMPL<4, FORM_PM>(jobs, njobs, groups, ngroups, __VA_ARGS__); \
+    case 26: return IMPL<5, FORM_GENERIC>(jobs, njobs, groups, ngroups, __VA_ARGS__); case 27: return IMPL<5, FORM_PM>(jobs, njobs, groups, ngroups, __VA_ARGS__); \
+    case 28: return IMPL<6, FORM_GENERIC>(jobs, njobs, groups, ngroups, __VA_ARGS__); case 29: return IMPL<6, FORM_PM>(jobs, njobs, groups, ngroups, __VA_ARGS__); \
+    case 30: return IMPL<7, FORM_GENERIC>(jobs, njobs, groups, ngroups, __VA_ARGS__); case 31: return IMPL<7, FORM_PM>(jobs, njobs, groups, ngroups, __VA_ARGS__); \
+    case 32: return IMPL<8, FORM_GENERIC>(jobs, njobs, groups, ngroups, __VA_ARGS__); case 33: return IMPL<8, FORM_PM>(jobs, njobs, groups, ngroups, __VA_ARGS__); \
     default: return cudaErrorInvalidValue;                                                \
     }
 cudaError_t launch_ntt_forward(const NttJob *jobs, u32 njobs, const NttRowGroup *groups, u32 ngroups, u32 logn, u32 form,
                                cudaStream_t st) {
     if (16 * ngroups > njobs) return cudaErrorInvalidValue;
-    ALOHA_NTT_DISPATCH(fwd_impl)
+    ALOHA_NTT_DISPATCH(fwd_impl, st)
 }
-cudaError_t launch_ntt_inverse(const NttJob *jobs, u32 njobs, u32 logn, u32 form, cudaStream_t st) {
-    const NttRowGroup *groups = nullptr;
-    const u32 ngroups = 0;
-    ALOHA_NTT_DISPATCH(inv_impl)
+cudaError_t launch_ntt_inverse(const NttJob *jobs, u32 njobs, const NttRowGroup *groups, u32 ngroups, const TmaMaps *maps,
+                               u32 logn, u32 form, cudaStream_t st) {
+    if (16 * ngroups > njobs || (ngroups && !maps)) return cudaErrorInvalidValue;
+    ALOHA_NTT_DISPATCH(inv_impl, maps, st)
 }
 
 }  // namespace alb
