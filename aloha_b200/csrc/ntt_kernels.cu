@@ -27,6 +27,12 @@
 // below 3q, bounds grow +3q per stage, and the reduction of an upper input is a fold at 2^60 (3
 // instructions, result below 2q) instead of a conditional subtract.  Same transform, same canonical
 // output words.
+//
+// The row passes exist twice: plain kernels (ntt_fwd_rows / ntt_inv_rows: rows loaded straight into
+// registers, twiddles through L1; any batch) and persistent TMA-staged ones (ntt_fwd_rows_tma /
+// ntt_inv_rows_tma) for batches that hold runs of 16 polynomials under one modulus -- rows, the row's
+// twiddle block and the group record are staged in shared memory by cp.async.bulk / cp.async.bulk.tensor
+// behind mbarriers, one tile ahead of the butterflies.
 #include <cstdlib>
 
 #include "kernels.cuh"
