@@ -128,3 +128,41 @@ def test_fuzz_fast_path(seed):
 @pytest.mark.parametrize("seed", range(100000, 100000 + int(os.environ.get("ALOHA_FUZZ_SEEDS", "24")) // 2))
 def test_fuzz_strict(seed):
     run_case(seed, strict=True, flags=A.F_STRICT | (A.F_DEFER if seed % 2 else 0))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_batched_transforms(seed):
+    """Random batch shapes through the transform launches: N, the number of polynomials (so the split between
+    the TMA-staged row passes, which take runs of 16 per modulus, and the plain ones varies), a random mix of
+    pseudo-Mersenne and generic moduli, inputs with q-1 runs and words in [q, 2q); forward then inverse, every
+    word against the oracle."""
+    rng = np.random.default_rng(4200 + seed)
+    n = 1 << int(rng.integers(8, 13))
+    rp = n // 128
+    B = int(rng.integers(1, 41))
+    n_pm, n_gen = int(rng.integers(0, 3)), int(rng.integers(0, 3))
+    if n_pm + n_gen == 0:
+        n_pm = 1
+    primes = O.synthetic_primes(n_pm, 2 * n) + O.synthetic_primes(n_gen, 2 * n, below=(1 << 60) - (1 << 40))
+    order = rng.permutation(len(primes))
+    primes = [primes[i] for i in order]
+    psis = [O.min_primitive_root(q, 2 * n) for q in primes]
+    L = len(primes)
+    rows = B * L * rp
+    flags = [0, A.F_GRAPHS, A.F_DEFER, A.F_GENERIC_MODMUL][seed % 4]
+    eng = A.Engine(vlmax_bits=n * 64, spm_rows=2 * rows, ksk_rows=0, moduli=list(zip(primes, psis)), flags=flags)
+    eng.load_isram(asm.transform_stream(n, primes).words(), 0)
+    eng.load_isram(asm.transform_stream(n, primes, inverse=True).words(), 1024)
+    qv = np.array(primes, dtype=np.uint64)[None, :, None]
+    x = rng.integers(0, 1 << 59, (B, L, n), dtype=np.uint64) % qv
+    x[0, :, : n // 2] = qv[0, :, :] - np.uint64(1)
+    x[B - 1, :, 1::2] += qv[0, :, :]                      # [q, 2q)
+    eng.dma_mem_h2d(0, x.reshape(-1))
+    eng.run_vp_batch(0, [(b * L * rp, 0, rows + b * L * rp, 0, 0) for b in range(B)])
+    F = eng.dma_mem_d2h(rows, B * L * n).reshape(B, L, n)
+    tabs = O.NttTables(n, primes, psis)
+    for b in range(B):
+        assert (F[b] == tabs.batch(x[b].copy(), np.arange(L))).all(), (seed, n, B, b)
+    eng.run_vp_batch(1024, [(rows + b * L * rp, 0, b * L * rp, 0, 0) for b in range(B)])
+    back = eng.dma_mem_d2h(0, B * L * n).reshape(B, L, n)
+    assert (back == x % qv).all(), (seed, n, B)
