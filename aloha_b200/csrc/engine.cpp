@@ -132,7 +132,7 @@ int get_tables(aloha *E, int mod, unsigned logn, const TwTable **out) {
     for (u64 r = 0; r < R; ++r)
         for (u32 u = 0; u < 8; ++u)
             for (u32 j = 0; j < (1u << u); ++j) {
-                fwd_rows[r * 256 + row_slot(u, j)] = fwd[((R + r) << u) + j];
+                fwd_rows[r * 256 + row_slot8(u, j)] = fwd[((R + r) << u) + j];
                 inv_rows[r * 256 + row_slot(u, j)] = inv[(1ull << (logn - 8 + u)) + (r << u) + j];
             }
     TwTable t;

@@ -48,7 +48,8 @@ struct NttJob {
                            // N/256 x 256 view: what one TMA copy stages for a tile (ntt_kernels.cu, row_slot)
     ModulusConsts mc;
 };
-// Slot of twiddle (level u, index j < 2^u) inside a row's 256-entry block of `rtw` (slot 0 unused).
+// Slot of twiddle (level u, index j < 2^u) inside a row's 256-entry block of `rtw` (slot 0 unused), as the
+// INVERSE row pass reads it (half-warp per row, 16 coefficients per thread; GS level lt = 7 - u).
 // Levels 0..3 are warp-uniform reads; levels 4..7 are read by lane h = j >> (u-4) with m = j mod 2^(u-4)
 // and are laid out [m][h] so that the 16 lanes of a half-warp read 16 consecutive entries.
 __host__ __device__ constexpr u32 row_slot(u32 u, u32 j) {
@@ -122,6 +123,17 @@ struct AutMacJob {
     const u64 *p;
     u64 q, iq, k, kinv;
 };
+
+// The forward row pass's layout of the same 256-entry block (a whole warp per row, 8 coefficients per
+// thread, phases of 3 + 3 + 2 levels): levels 0..2 warp-uniform; 3..5 read by lane group hi = lane / 4,
+// laid out [m][hi]; 6..7 read by lane T, laid out [m][T].
+__host__ __device__ constexpr u32 row_slot8(u32 u, u32 j) {
+    return u < 4 ? (1u << u) + j
+         : u == 4 ? 16 + (j & 1) * 8 + (j >> 1)
+         : u == 5 ? 32 + (j & 3) * 8 + (j >> 2)
+         : u == 6 ? 64 + (j & 1) * 32 + (j >> 1)
+                  : 128 + (j & 3) * 32 + (j >> 2);
+}
 
 // 16 jobs of one direction that share a modulus (and load op), as the TMA-staged row passes want them:
 // one record is one bulk copy.  `src` is what the row pass reads -- forward: the column pass's output

@@ -45,13 +45,13 @@
 #define COLS_MINB 3
 #endif
 #ifndef ROWS_TMA_MINB
-#define ROWS_TMA_MINB 4      /* CTAs of 16 * ROWS_TMA_TILE threads per SM */
+#define ROWS_TMA_MINB 4      /* staged inverse row pass: CTAs of 16 * ROWS_TMA_TILE threads per SM */
 #endif
 #ifndef ROWS_TMA_STAGES
 #define ROWS_TMA_STAGES 2
 #endif
 #ifndef ROWS_TMA_TILE
-#define ROWS_TMA_TILE 8      /* rows (= half-warps) per tile and CTA: 8 or 16 */
+#define ROWS_TMA_TILE 8      /* staged inverse row pass: rows (= half-warps) per tile and CTA, 8 or 16 */
 #endif
 
 namespace alb {
@@ -274,30 +274,12 @@ __global__ void __launch_bounds__(256, ROWS_MINB) ntt_fwd_rows(const NttJob *__r
     }
 }
 
-// ============================================================================ forward: rows, TMA-staged
-// Persistent variant of the row pass for launches that hold many polynomials per modulus (the batched
-// configs).  One tile = row r of 16 polynomials that share a modulus (one NttRowGroup): the 16 rows
-// (16 x 2 KiB), the row's 256 twiddles in read order (4 KiB, NttJob::rtw) and the group record are staged
-// in shared memory by cp.async.bulk (TMA) into a ring of kStages stages, each armed with an mbarrier, so
-// the loads of tile i+kStages run under the butterflies of the tiles before it.  There is no block-wide
-// barrier: a warp that is done with a stage's shared memory counts itself out, and the last one out
-// refills the stage.  The twiddles of a tile are read from shared memory by all 16 half-warps instead of
-// 16 times from L1/L2, and the mid-transform exchange happens in place in the half-warp's own staged row
-// slot (padded to 288 words).  A CTA is kTileRows / 2 warps; with 8-row tiles a stage is 22.3 KiB and
-// four CTAs fit on an SM.  Measured alternatives, none faster: 16-row tiles (4 % slower -- more warps
-// wait on each other's stage), three stages, 80 registers for more CTAs, an XOR-swizzled 2 KiB slot,
-// refilling the rows half a tile earlier than the twiddles.
+// ============================================================================ TMA staging helpers
+// The persistent row passes stage their tiles in shared memory with cp.async.bulk / cp.async.bulk.tensor
+// (TMA) behind mbarriers; kStages tiles are in flight per CTA.
 constexpr int kStages = ROWS_TMA_STAGES;
-constexpr int kTileRows = ROWS_TMA_TILE;          // a group of 16 polynomials is 16 / kTileRows tiles per row index
+constexpr int kTileRows = ROWS_TMA_TILE;          // inverse pass: rows (= half-warps) per tile
 constexpr int kTilesPerGroupRow = 16 / kTileRows;
-struct RowsSmem {
-    u64 data[kStages][kTileRows][kRowPad];   // a staged row is 256 words; the exchange uses the padded 288
-    Tw tw[kStages][256];
-    NttRowGroup grp[kStages];
-    u64 full[kStages];
-    u32 done[kStages];
-};
-static_assert(sizeof(RowsSmem) <= (233472 - ROWS_TMA_MINB * 1024) / ROWS_TMA_MINB, "ROWS_TMA_MINB CTAs per SM");
 
 __device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
@@ -326,16 +308,43 @@ __device__ __forceinline__ Tw ldtw_s(const Tw *p) {
     return t;
 }
 
+// ============================================================================ forward: rows, TMA-staged
+// Persistent variant of the row pass for launches that hold many polynomials per modulus (the batched
+// configs).  One tile = row r of kTileRows8 polynomials that share a modulus (a quarter of an
+// NttRowGroup): the rows (2 KiB each, from different polynomials), the row's 256 twiddles in read order
+// (4 KiB, NttJob::rtw, row_slot8) and the group record are staged in shared memory by cp.async.bulk (TMA)
+// into a ring of kStages stages, each armed with an mbarrier, so the loads of tile i+kStages run under
+// the butterflies of the tiles before it.  There is no block-wide barrier: a warp that is done with a
+// stage's shared memory counts itself out, and the last one out refills the stage.
+// A whole warp per row, 8 coefficients per thread: levels 0..2 on elements lane + 32 k, exchange, levels
+// 3..5 on elements hi*32 + m*4 + lo (lane = hi*4 + lo), exchange, levels 6..7 on elements 8 lane + e.
+// Both exchanges run in place in the row's staged slot, padded to 288 words (word jj at jj + 2 (jj >> 4)):
+// conflict-free for all four access patterns.  64 registers: 8 CTAs of 4 warps per SM.  (The previous
+// version -- a half-warp per row, 16 coefficients per thread, 96 registers, one exchange -- had the same
+// instruction count per butterfly but half the resident warps, and this pass is limited by warps waiting
+// on each other's stage and on dependent integer latency, not by issue: 1.71 -> 1.77 M limb-NTT/s.
+// Also measured, none faster: 16- and 4-row tiles of the old shape, a third stage, an XOR-swizzled 2 KiB
+// slot, refilling the rows half a tile before the twiddles, prefetching the refill's source addresses.)
+constexpr int kTileRows8 = 4;
+constexpr int kTilesPerGroupRow8 = 16 / kTileRows8;
+struct FwdRowsSmem {
+    u64 data[kStages][kTileRows8][kRowPad];
+    Tw tw[kStages][256];
+    NttRowGroup grp[kStages];
+    u64 full[kStages];
+    u32 done[kStages];
+};
+static_assert((sizeof(FwdRowsSmem) + 1024) * 8 <= 233472, "eight CTAs per SM");
 #undef ALOHA_LDTW
 #define ALOHA_LDTW ldtw_s
 template <int S1, int FORM>
-__global__ void __launch_bounds__(16 * kTileRows, ROWS_TMA_MINB) ntt_fwd_rows_tma(const NttRowGroup *__restrict__ groups, u32 ntiles) {
+__global__ void __launch_bounds__(32 * kTileRows8, 8) ntt_fwd_rows_tma(const NttRowGroup *__restrict__ groups, u32 ntiles) {
     typedef Arith<FORM> AR;
     constexpr int R = 1 << S1;
-    constexpr u32 kStageBytes = kTileRows * 2048 + 256 * sizeof(Tw) + sizeof(NttRowGroup);
+    constexpr u32 kStageBytes = kTileRows8 * 2048 + 256 * sizeof(Tw) + sizeof(NttRowGroup);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    RowsSmem &S = *reinterpret_cast<RowsSmem *>(smem_raw);
-    const int t = threadIdx.x, lane = t & 31, hw = t >> 4, h = t & 15;
+    FwdRowsSmem &S = *reinterpret_cast<FwdRowsSmem *>(smem_raw);
+    const int t = threadIdx.x, lane = t & 31, wr = t >> 5, hi = lane >> 2, lo = lane & 3;
     if (t == 0) {
         for (int b = 0; b < kStages; ++b) {
             mbar_init(&S.full[b], 1);
@@ -344,15 +353,13 @@ __global__ void __launch_bounds__(16 * kTileRows, ROWS_TMA_MINB) ntt_fwd_rows_tm
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // one whole warp: arm stage b and start the copies of `tile` into it
-    // tile -> (group, row index r, which kTileRows of the group's 16 polynomials)
     auto stage_in = [&](u32 tile, int b) {
-        const u32 sub = tile % kTilesPerGroupRow, gr = tile / kTilesPerGroupRow;
+        const u32 sub = tile % kTilesPerGroupRow8, gr = tile / kTilesPerGroupRow8;
         const NttRowGroup *G = groups + gr / R;
         const size_t off = (size_t)(gr % R) * 256;
         if (lane == 0) mbar_arrive_expect_tx(&S.full[b], kStageBytes);
         __syncwarp();
-        if (lane < kTileRows) bulk_g2s(&S.data[b][lane][0], G->src[sub * kTileRows + lane] + off, 2048, &S.full[b]);
+        if (lane < kTileRows8) bulk_g2s(&S.data[b][lane][0], G->src[sub * kTileRows8 + lane] + off, 2048, &S.full[b]);
         else if (lane == 16) bulk_g2s(&S.tw[b][0], G->rtw + off, 256 * sizeof(Tw), &S.full[b]);
         else if (lane == 17) bulk_g2s(&S.grp[b], G, sizeof(NttRowGroup), &S.full[b]);
     };
@@ -366,58 +373,65 @@ __global__ void __launch_bounds__(16 * kTileRows, ROWS_TMA_MINB) ntt_fwd_rows_tm
         mbar_wait(&S.full[b], parity);
         const NttRowGroup &G = S.grp[b];
         const AR A(G.mc);
-        u64 *dst = G.dst[(tile % kTilesPerGroupRow) * kTileRows + hw] + (size_t)(tile / kTilesPerGroupRow % R) * 256;
+        u64 *dst = G.dst[(tile % kTilesPerGroupRow8) * kTileRows8 + wr] + (size_t)(tile / kTilesPerGroupRow8 % R) * 256;
         const Tw *tw = S.tw[b];
-        u64 *row = &S.data[b][hw][0];
+        u64 *row = &S.data[b][wr][0];
 
-        u64 x[16];
+        u64 x[8];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = row[h + 16 * k];
-        __syncwarp();                      // the row is in registers: its 2 KiB are the exchange buffer now
+        for (int k = 0; k < 8; ++k) x[k] = row[lane + 32 * k];
+        __syncwarp();                      // the row is in registers: its slot is the exchange buffer now
         if (S1 == 0 && G.mc.pre) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) x[k] = apply_pre(x[k], G.mc.pre, A);
+            for (int k = 0; k < 8; ++k) x[k] = apply_pre(x[k], G.mc.pre, A);
         }
         int B = cols_out_bound<FORM>(S1);
-        // phase A: level u pairs k-bit (3-u); twiddle j = k >> (4 - u), warp-uniform
+        // phase A: level u pairs k-bit (2-u); twiddle j = k >> (3 - u), warp-uniform
 #pragma unroll
-        for (int u = 0; u < 4; ++u) ALOHA_CT_STAGE(16, 8 >> u, row_slot(u, g0 >> (4 - u)))
-        // exchange h + 16 k -> 16 h + e, in place in the half-warp's own staged row
-        // word jj at jj + 2 (jj >> 4): strided writes and 16-byte reads both conflict-free, all offsets immediates
+        for (int u = 0; u < 3; ++u) ALOHA_CT_STAGE(8, 4 >> u, row_slot8(u, g0 >> (3 - u)))
+        // exchange: lane + 32 k  ->  hi*32 + m*4 + lo
+        u64 *wa = row + lane + 2 * (lane >> 4);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) row[h + 18 * k] = x[k];
+        for (int k = 0; k < 8; ++k) wa[36 * k] = x[k];
         __syncwarp();
+        u64 *rb = row + 36 * hi + lo;
 #pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(row + 18 * h + e);
-            x[e] = v.x;
-            x[e + 1] = v.y;
+        for (int m = 0; m < 8; ++m) x[m] = rb[4 * m + 2 * (m >> 2)];
+        // phase B: level u = 3 + v pairs m-bit (2-v); twiddle j = (hi << v) + (m >> (3 - v))
+#pragma unroll
+        for (int v = 0; v < 3; ++v) ALOHA_CT_STAGE(8, 4 >> v, row_slot8(3 + v, (hi << v) + (g0 >> (3 - v))))
+        // exchange: hi*32 + m*4 + lo  ->  8 lane + e   (every lane has read its phase-B inputs: same words)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) rb[4 * m + 2 * (m >> 2)] = x[m];
+        __syncwarp();
+        u64 *rc = row + 8 * lane + 2 * (lane >> 1);
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+            const ulonglong2 v2 = *reinterpret_cast<const ulonglong2 *>(rc + e);
+            x[e] = v2.x;
+            x[e + 1] = v2.y;
         }
-        // phase B: level u pairs e-bit (7-u); twiddle j = (16 h + e) >> (8 - u)
+        // phase C: level u = 6 + v pairs e-bit (1-v); twiddle j = (lane << (v + 1)) + (e >> (2 - v))
 #pragma unroll
-        for (int u = 4; u < 8; ++u) ALOHA_CT_STAGE(16, 128 >> u, row_slot(u, (16 * h + g0) >> (8 - u)))
-        // Done with stage b's shared memory (the results are in registers).  Its rows were written through
-        // the generic proxy: order that before the TMA that refills them.  The last warp out resets the
-        // count and stages the tile kStages steps ahead.  This comes BEFORE the global stores, so the
-        // fence does not wait for them.
+        for (int v = 0; v < 2; ++v) ALOHA_CT_STAGE(8, 2 >> v, row_slot8(6 + v, (lane << (v + 1)) + (g0 >> (2 - v))))
+        // leave the stage, then canonical values and 16-byte stores (see ntt_fwd_rows_tma)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         u32 last = 0;
         if (lane == 0) {
-            last = atomicAdd(&S.done[b], 1u) == kTileRows / 2 - 1;   // kTileRows / 2 warps share the stage
+            last = atomicAdd(&S.done[b], 1u) == kTileRows8 - 1;
             if (last) S.done[b] = 0;
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last && tile + kStages * stride < ntiles) stage_in(tile + kStages * stride, b);
-        // 16-byte stores whose four words are selected straight into the store's register quad
 #pragma unroll
-        for (int e = 0; e < 16; e += 2) {
+        for (int e = 0; e < 8; e += 2) {
             const u64 a0 = A.canon_lazy(x[e]), a1 = A.canon_lazy(x[e + 1]);     // below 2q
             const u64 b0 = a0 - A.q, b1 = a1 - A.q;
             const bool n0 = (long long)b0 < 0, n1 = (long long)b1 < 0;
             const u32 w0 = n0 ? (u32)a0 : (u32)b0, w1 = n0 ? (u32)(a0 >> 32) : (u32)(b0 >> 32);
             const u32 w2 = n1 ? (u32)a1 : (u32)b1, w3 = n1 ? (u32)(a1 >> 32) : (u32)(b1 >> 32);
-            asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 16 * h + e), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+            asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 8 * lane + e), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
         }
         if (++b == kStages) { b = 0; parity ^= 1; }
     }
@@ -728,13 +742,13 @@ static cudaError_t fwd_impl(const NttJob *jobs, u32 njobs, const NttRowGroup *gr
     if (ngroups) {
         static int resident = 0;            // CTAs of the persistent row pass that fit on one SM
         if (!resident) {
-            cudaError_t e = cudaFuncSetAttribute(ntt_fwd_rows_tma<S1, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsSmem));
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ntt_fwd_rows_tma<S1, FORM>, 16 * kTileRows, sizeof(RowsSmem));
+            cudaError_t e = cudaFuncSetAttribute(ntt_fwd_rows_tma<S1, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdRowsSmem));
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ntt_fwd_rows_tma<S1, FORM>, 32 * kTileRows8, sizeof(FwdRowsSmem));
             if (e != cudaSuccess) return e;
             if (resident < 1) return cudaErrorLaunchOutOfResources;
         }
-        const u32 tiles = ngroups * R * kTilesPerGroupRow, ctas = (u32)(resident * sm_count());
-        ntt_fwd_rows_tma<S1, FORM><<<tiles < ctas ? tiles : ctas, 16 * kTileRows, sizeof(RowsSmem), st>>>(groups, tiles);
+        const u32 tiles = ngroups * R * kTilesPerGroupRow8, ctas = (u32)(resident * sm_count());
+        ntt_fwd_rows_tma<S1, FORM><<<tiles < ctas ? tiles : ctas, 32 * kTileRows8, sizeof(FwdRowsSmem), st>>>(groups, tiles);
         count_launch();
     }
     if (njobs > 16 * ngroups) {
