@@ -387,7 +387,7 @@ def run_gpu(args):
                          "co_bound": {"what": "integer issue: the butterflies alone (registers only, no memory; tools/bf_bench.cu) run at "
                                               "4.09 butterflies/clk/SM with the pseudo-Mersenne product (3.02 with Shoup's), i.e. the "
                                               "arithmetic caps this two-pass transform at 2.27 M limb-NTTs/s; the board's 600 W software "
-                                              "power cap holds the sustained figure a further 7 % under the burst one",
+                                              "power cap holds the sustained figure ~7 % under the burst one",
                                       "arithmetic_only_ceiling_limb_ntts_per_s": 2.27e6,
                                       "arithmetic_only_ceiling_generic_primes_limb_ntts_per_s": 1.67e6,
                                       "see": "DESIGN.md section 5"},
