@@ -107,6 +107,16 @@ def rotate_mac_stream(n: int, moduli: list[int]) -> Program:
     return p.brk()
 
 
+def vaut_stream(n: int, moduli: list[int]) -> Program:
+    """Standalone automorphism per limb: rslt[l] = aut_k(src0[l]); k comes from the step CSR
+    (the VAUT steps of keyswitch.mem, insts 5, 20, ... on their own)."""
+    p = Program().vsetvl(n)
+    rp = rows_per_poly(n)
+    for l, q in enumerate(moduli):
+        p.vsetq(q).vle(0, BASE_SRC0, l * rp).vaut(2, 0).vse(2, BASE_RSLT, l * rp)
+    return p.brk()
+
+
 def elementwise_stream(n: int, moduli: list[int], op: str, scalar: int | None = None) -> Program:
     """mul_plain / hom_add generalised: rslt[l] = src0[l] (op) src1[l]  (or scalar)."""
     p = Program().vsetvl(n)

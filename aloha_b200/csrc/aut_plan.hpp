@@ -1,0 +1,226 @@
+// aut_plan.hpp -- tile decomposition of the Galois permutation d = i*k mod n (VAUT), shared by the host
+// planner, the CUDA kernels (ew_kernels.cu) and the CPU test that replays the kernels' index arithmetic
+// (tests/native/aut_plan_model.cpp).
+//
+// Replaces the address generation of src/vp/vxu/vxu_lane.sv:594-599 (dst address = (i*k) mod N, sign from
+// (i*k) mod 2N) and the lane interconnect that carries it out 128 lanes per cycle
+// (src/vp/iconn/iconn_top.sv:72-138).
+//
+// The permutation destroys locality at word granularity: neighbours in the source (i, i+1) land k apart,
+// neighbours in the destination (d, d+1) come from sources k^-1 apart.  A tile that is contiguous on both
+// sides is a parallelogram of the lattice {(j, f) -> d = j*k + f}:  +1 in j is +1 in the SOURCE, +1 in f is
+// +1 in the DESTINATION.  (Boxes [0,J) x [0,F) never tile Z_n exactly for odd k, so the cover is built from
+// the three-distance structure instead.)
+//
+//   Take the J points j*k mod n, j < J, on the circle Z_n.  For J = u + v, where u*k mod n = alpha is the
+//   smallest positive residue among j < J and n - v*k mod n = beta the smallest negative one, the points cut
+//   the circle into exactly two arc lengths: point j < v is followed by point j + u (arc alpha), point
+//   j >= v by point j - v (arc beta);  v*alpha + u*beta = n.  Every destination d lies on exactly one arc:
+//       d = (j*k + f) mod n,  0 <= f < arc(j)      <->      source i = (j + f*kinv) mod n.
+//   So Z_n is covered exactly once by two rectangles of (j, f) pairs: class A = [0,v) x [0,alpha) and
+//   class B = [v,J) x [0,beta).  All (u, alpha, v, beta) configurations come out of the subtractive
+//   Euclidean algorithm on (k mod n, n); the planner walks them, replays one tile of each class and keeps
+//   the configuration that touches the fewest 32-byte sectors per element on both sides.
+//
+//   A tile is JB consecutive j times FB consecutive f of one class (JB * FB <= 2048, chosen per class).
+//   Loading it reads, for each f, the JB consecutive source words starting at j0 + f*kinv; storing it
+//   writes, for each j, the FB consecutive destination words starting at j*k + f0.  The transposition
+//   happens in shared memory.  Thin rectangles stay coalesced because the lattice is self-dual: when a class
+//   has few points, consecutive f rows are (nearly) adjacent in the source, and vice versa.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define ALOHA_HD __host__ __device__ __forceinline__
+#else
+#define ALOHA_HD inline
+#endif
+
+namespace alb {
+
+constexpr unsigned kAutTileLog = 11;                 // 2048 words = 16 KiB per tile
+constexpr unsigned kAutTile = 1u << kAutTileLog;
+constexpr unsigned kAutSmemWords = kAutTile + 1024;  // worst-case padding: FB rows * 1 word (FB <= 1024)
+constexpr unsigned kAutThreads = 256;
+
+struct AutClass {
+    uint32_t j_begin, j_end;   // points of this class
+    uint32_t gap;              // arc length
+    uint32_t log_jb, log_fb;   // tile = 2^log_jb points x 2^log_fb offsets
+    uint32_t fblocks;          // f-blocks per j-block
+    uint32_t stride;           // shared-memory row stride in words (row = one f)
+    uint32_t tile_begin;       // first tile id of this class
+};
+
+struct AutPlan {
+    uint32_t mask;             // n - 1
+    uint32_t kmod, kinv;       // k mod n, k^-1 mod n
+    uint32_t ntiles;
+    AutClass cls[2];           // A then B
+};
+
+struct AutTile {
+    uint32_t j0, jcount, f0, fcount;
+    uint32_t log_jb, log_fb, stride;
+};
+
+ALOHA_HD AutTile aut_tile(const AutPlan &p, uint32_t tile) {
+    const AutClass &c = p.cls[tile >= p.cls[1].tile_begin ? 1 : 0];
+    tile -= c.tile_begin;
+    const uint32_t jb = tile / c.fblocks, fb = tile - jb * c.fblocks;
+    AutTile t;
+    t.log_jb = c.log_jb; t.log_fb = c.log_fb; t.stride = c.stride;
+    t.j0 = c.j_begin + (jb << c.log_jb);
+    t.f0 = fb << c.log_fb;
+    const uint32_t jb_size = 1u << c.log_jb, fb_size = 1u << c.log_fb;
+    t.jcount = c.j_end - t.j0 < jb_size ? c.j_end - t.j0 : jb_size;
+    t.fcount = c.gap - t.f0 < fb_size ? c.gap - t.f0 : fb_size;
+    return t;
+}
+// source / destination index of element (jl, fl) of a tile
+ALOHA_HD uint32_t aut_src(const AutPlan &p, const AutTile &t, uint32_t jl, uint32_t fl) {
+    return (t.j0 + jl + (t.f0 + fl) * p.kinv) & p.mask;
+}
+ALOHA_HD uint32_t aut_dst(const AutPlan &p, const AutTile &t, uint32_t jl, uint32_t fl) {
+    return ((t.j0 + jl) * p.kmod + t.f0 + fl) & p.mask;
+}
+// which (jl, fl) a thread's slot s addresses in the load phase (lanes along j) / store phase (lanes along f)
+ALOHA_HD void aut_load_slot(const AutTile &t, uint32_t s, uint32_t *jl, uint32_t *fl) {
+    *fl = s >> t.log_jb; *jl = s & ((1u << t.log_jb) - 1);
+}
+ALOHA_HD void aut_store_slot(const AutTile &t, uint32_t s, uint32_t *jl, uint32_t *fl) {
+    *jl = s >> t.log_fb; *fl = s & ((1u << t.log_fb) - 1);
+}
+
+namespace autdetail {
+
+inline uint32_t clog2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) ++l; return l; }
+
+// tile shape and padding for a class of `count` points with arc `gap`
+inline void shape_class(AutClass &c) {
+    const uint32_t count = c.j_end - c.j_begin, lj = clog2(count ? count : 1), lf = clog2(c.gap ? c.gap : 1);
+    uint32_t log_jb, log_fb;
+    if (lj + lf <= kAutTileLog) { log_jb = lj; log_fb = lf; }
+    else {
+        log_fb = lf < 6 ? lf : 6;                        // prefer 64-word destination runs ...
+        log_jb = kAutTileLog - log_fb < lj ? kAutTileLog - log_fb : lj;
+        if (log_jb + log_fb < kAutTileLog)               // ... unless there are too few points: lengthen the f side
+            log_fb = kAutTileLog - log_jb < lf ? kAutTileLog - log_jb : lf;
+    }
+    if (log_fb > 10) log_fb = 10;                        // shared-memory padding budget (kAutSmemWords)
+    c.log_jb = log_jb;
+    c.log_fb = log_fb;
+    const uint32_t JB = 1u << log_jb, FB = 1u << log_fb;
+    c.fblocks = c.gap ? (c.gap + FB - 1) / FB : 0;
+    // row stride: the store phase reads element (jl, fl) with fl fastest; 16 consecutive lanes must fall on
+    // 16 different 8-byte banks.  FB >= 16: an odd stride; 1 < FB < 16: stride = 16 / FB (mod 32 / FB).
+    if (FB >= 16) c.stride = JB | 1;
+    else if (FB == 1) c.stride = JB;
+    else {
+        const uint32_t m = 32 / FB, r = 16 / FB;
+        c.stride = JB + (r + m - JB % m) % m;
+    }
+}
+
+inline uint32_t class_tiles(const AutClass &c) {
+    const uint32_t count = c.j_end - c.j_begin;
+    return count && c.gap ? ((count + (1u << c.log_jb) - 1) >> c.log_jb) * c.fblocks : 0;
+}
+
+inline void finish(AutPlan &p) {
+    shape_class(p.cls[0]);
+    shape_class(p.cls[1]);
+    p.cls[0].tile_begin = 0;
+    p.cls[1].tile_begin = class_tiles(p.cls[0]);
+    p.ntiles = p.cls[1].tile_begin + class_tiles(p.cls[1]);
+}
+
+// 32-byte sectors touched by the warp instructions of one tile (both phases) and the elements it holds
+inline void tile_cost(const AutPlan &p, uint32_t tile, uint64_t *sectors, uint64_t *elements, uint64_t *winstr) {
+    const AutTile t = aut_tile(p, tile);
+    const uint32_t slots = 1u << (t.log_jb + t.log_fb);
+    for (int phase = 0; phase < 2; ++phase)
+        for (uint32_t base = 0; base < slots; base += 32) {
+            uint32_t sec[32], ns = 0;
+            for (uint32_t lane = 0; lane < 32 && base + lane < slots; ++lane) {
+                uint32_t jl, fl;
+                if (phase == 0) aut_load_slot(t, base + lane, &jl, &fl); else aut_store_slot(t, base + lane, &jl, &fl);
+                if (jl >= t.jcount || fl >= t.fcount) continue;
+                const uint32_t a = (phase == 0 ? aut_src(p, t, jl, fl) : aut_dst(p, t, jl, fl)) >> 2;
+                bool dup = false;
+                for (uint32_t e = 0; e < ns && !dup; ++e) dup = sec[e] == a;
+                if (!dup) sec[ns++] = a;
+                if (phase == 0) ++*elements;
+            }
+            *sectors += ns;
+            *winstr += ns ? 1 : 0;
+        }
+}
+
+}  // namespace autdetail
+
+// Host: choose the configuration and the tile shapes for (n, k).  k odd, n a power of two >= 4.
+inline AutPlan make_aut_plan(uint32_t n, uint64_t k) {
+    AutPlan base{};
+    base.mask = n - 1;
+    base.kmod = (uint32_t)(k & (n - 1));
+    uint64_t inv = k;                                   // Newton: k^-1 mod 2^64
+    for (int i = 0; i < 6; ++i) inv *= 2 - k * inv;
+    base.kinv = (uint32_t)(inv & (n - 1));
+    auto build = [&](uint64_t u, uint64_t alpha, uint64_t v, uint64_t beta) {
+        AutPlan p = base;
+        p.cls[0].j_begin = 0; p.cls[0].j_end = (uint32_t)v; p.cls[0].gap = (uint32_t)alpha;
+        p.cls[1].j_begin = (uint32_t)v; p.cls[1].j_end = (uint32_t)(u + v); p.cls[1].gap = (uint32_t)beta;
+        autdetail::finish(p);
+        return p;
+    };
+    // Estimated cost of a configuration: sectors per element (1/4 is ideal on each side) from replaying the
+    // first tile of each class, weighted by the class's share of the elements, plus a small charge per warp
+    // instruction so that sparse tiles lose against full ones.
+    auto cost = [&](const AutPlan &p) {
+        double total = 0;
+        for (int c = 0; c < 2; ++c) {
+            const AutClass &C = p.cls[c];
+            const double share = (double)(C.j_end - C.j_begin) * C.gap / n;
+            if (share == 0) continue;
+            uint64_t sec = 0, el = 0, wi = 0;
+            autdetail::tile_cost(p, C.tile_begin, &sec, &el, &wi);
+            total += share * ((double)sec + 0.5 * (double)wi) / (double)el;
+        }
+        return total;
+    };
+    // Subtractive Euclid over (u, alpha), (v, beta).  Inside a run of equal steps the states change linearly,
+    // so they are sampled geometrically (1, 2, 4, ... steps into the run, and its last two states).
+    uint64_t u = 1, alpha = base.kmod, v = 1, beta = n - base.kmod;
+    AutPlan best = build(u, alpha, v, beta);
+    double best_cost = cost(best);
+    auto consider = [&](uint64_t cu, uint64_t ca, uint64_t cv, uint64_t cb) {
+        const AutPlan p = build(cu, ca, cv, cb);
+        const double c = cost(p);
+        if (c < best_cost) { best_cost = c; best = p; }
+    };
+    while (!(alpha == 1 && beta == 1)) {
+        if (alpha > beta) {
+            const uint64_t steps = (alpha - 1) / beta;           // alpha stays >= 1
+            for (uint64_t t = 1;; t *= 2) {
+                const uint64_t s = t < steps ? t : steps;
+                consider(u + s * v, alpha - s * beta, v, beta);
+                if (s == steps) break;
+            }
+            if (steps > 1) consider(u + (steps - 1) * v, alpha - (steps - 1) * beta, v, beta);
+            u += steps * v; alpha -= steps * beta;
+        } else {
+            const uint64_t steps = (beta - 1) / alpha;
+            for (uint64_t t = 1;; t *= 2) {
+                const uint64_t s = t < steps ? t : steps;
+                consider(u, alpha, v + s * u, beta - s * alpha);
+                if (s == steps) break;
+            }
+            if (steps > 1) consider(u, alpha, v + (steps - 1) * u, beta - (steps - 1) * alpha);
+            v += steps * u; beta -= steps * alpha;
+        }
+    }
+    return best;
+}
+
+}  // namespace alb

@@ -171,6 +171,14 @@ void free_plans(aloha *E) {
     E->plans.clear();
 }
 
+// Tile decomposition of the Galois permutation for (n, k), built once per pair.
+const AutPlan &aut_plan_for(aloha *E, u32 n, u64 k) {
+    auto key = std::make_pair((uint32_t)n, (uint64_t)k);
+    auto it = E->aut_plans.find(key);
+    if (it == E->aut_plans.end()) it = E->aut_plans.emplace(key, make_aut_plan(n, k)).first;
+    return it->second;
+}
+
 inline bool overlap(const u64 *a, u64 an, const u64 *b, u64 bn) {
     return a && b && a < b + bn && b < a + an;
 }
@@ -552,6 +560,10 @@ size_t fuse_ops(std::vector<VecOp> &ops, const Loc *final_loc, const aloha *E) {
                     clobbered = true;
             if (clobbered) continue;
             const u64 *addend = side == 0 ? add.b : add.a;
+            // index-preserving fused kernels may run in place on an operand, but only on exactly the same
+            // range: a partial overlap would read words another thread has already replaced
+            auto partial = [&](const u64 *p) { return p != add.dst && overlap(add.dst, add.n, p, add.n); };
+            if (partial(mul.a) || partial(mul.b) || partial(addend)) continue;
             // is one multiplicand a single-use, dead automorphism output?
             int pa = -1;
             const u64 *other = nullptr;
@@ -561,6 +573,9 @@ size_t fuse_ops(std::vector<VecOp> &ops, const Loc *final_loc, const aloha *E) {
                     bool bad = false;
                     for (size_t j = cand + 1; j < i && !bad; ++j)
                         if (!ops[j].dead && overlap(ops[j].dst, ops[j].n, ops[cand].a, ops[cand].n)) bad = true;
+                    // the fused kernel gathers x while other threads store dst: they must not share words
+                    // (store forwarding may already have pointed the add at the SPM range x lives in)
+                    if (overlap(add.dst, add.n, ops[cand].a, ops[cand].n)) bad = true;
                     if (!bad) { pa = cand; other = ms == 0 ? mul.b : mul.a; }
                 }
             }
@@ -640,6 +655,9 @@ size_t fuse_ops(std::vector<VecOp> &ops, const Loc *final_loc, const aloha *E) {
                 for (auto &tm : terms)
                     if (overlap(ops[j].dst, ops[j].n, tm.first, o.n) || overlap(ops[j].dst, ops[j].n, tm.second, o.n)) { clobbered = true; break; }
             }
+            for (auto &tm : terms)
+                if ((tm.first != o.dst && overlap(o.dst, o.n, tm.first, o.n)) || (tm.second != o.dst && overlap(o.dst, o.n, tm.second, o.n)))
+                    clobbered = true;
             if (clobbered) continue;
             terms.emplace_back(o.a, o.b);
             o.kind = K_SOP;
@@ -780,8 +798,20 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
                     sop_jobs.emplace_back(at, &o);
                     break;
                 }
-                case K_AUTMAC: append(tables, AutMacJob{o.dst, o.c, o.a, o.b, o.q, o.iq, o.k, o.kinv}); break;
+                case K_AUTMAC: {
+                    const AutPlan &ap = aut_plan_for(E, o.n, o.k);
+                    L.aux = std::max(L.aux, ap.ntiles);
+                    append(tables, AutMacJob{o.dst, o.c, o.a, o.b, o.q, o.iq, o.k, o.kinv, ap});
+                    break;
+                }
                 case K_VAUT:
+                    if (!(E->cfg.flags & ALOHA_F_AUT_GATHER)) {
+                        const AutPlan &ap = aut_plan_for(E, o.n, o.k);
+                        L.aux = std::max(L.aux, ap.ntiles);
+                        append(tables, AutJob{o.dst, o.a, o.q, o.k, ap});
+                        break;
+                    }
+                    [[fallthrough]];
                 case K_VROLI: append(tables, PermJob{o.dst, o.a, o.q, o.k, o.kinv}); break;
                 case K_NTT:
                 case K_INTT: {
@@ -859,8 +889,14 @@ int issue(aloha *E, const Plan &plan, u64 *launched) {
         case K_PEASE_I: e = launch_pease((const PeaseJob *)tab, L.njobs, ilog2(L.n), L.alu, true, E->stream); break;
         case K_MULADD: e = launch_muladd((const MulAddJob *)tab, L.njobs, L.n, E->stream); break;
         case K_SOP: e = launch_sop((const SopJob *)tab, L.njobs, L.n, E->stream); break;
-        case K_AUTMAC: e = launch_autmac((const AutMacJob *)tab, L.njobs, L.n, E->stream); break;
-        case K_VAUT: e = launch_vaut((const PermJob *)tab, L.njobs, L.n, E->stream); break;
+        case K_AUTMAC:
+            e = (E->cfg.flags & ALOHA_F_AUT_GATHER) ? launch_autmac((const AutMacJob *)tab, L.njobs, L.n, E->stream)
+                                                    : launch_autmac_tiled((const AutMacJob *)tab, L.njobs, L.n, L.aux, E->stream);
+            break;
+        case K_VAUT:
+            e = (E->cfg.flags & ALOHA_F_AUT_GATHER) ? launch_vaut((const PermJob *)tab, L.njobs, L.n, E->stream)
+                                                    : launch_vaut_tiled((const AutJob *)tab, L.njobs, L.n, L.aux, E->stream);
+            break;
         case K_VROLI: e = launch_vroli((const PermJob *)tab, L.njobs, L.n, E->stream); break;
         case K_NTT: e = launch_ntt_forward((const NttJob *)tab, L.njobs, (const NttRowGroup *)(base + L.group_off), L.ngroups, ilog2(L.n), L.alu, E->stream); break;
         case K_INTT: e = launch_ntt_inverse((const NttJob *)tab, L.njobs, (const NttRowGroup *)(base + L.group_off), L.ngroups, &E->tma_maps, ilog2(L.n), L.alu, E->stream); break;

@@ -62,6 +62,7 @@ struct Launch {
     size_t table_off;   // byte offset of the job table inside the plan's device buffer
     u32 ngroups = 0;    // K_NTT: the first 16 * ngroups jobs are same-modulus runs of 16, described by the
     size_t group_off = 0;   //        NttRowGroup records at this offset (kernels.cuh launch_ntt_forward)
+    u32 aux = 0;        // K_VAUT / K_AUTMAC (tiled): the largest tile count among the launch's jobs
 };
 
 struct TwTable {
@@ -114,6 +115,7 @@ struct aloha {
     uint64_t isram_version = 0, tf_version = 0;
     std::vector<alb::u64> mod_q, mod_psi;
     std::map<std::pair<int, unsigned>, alb::TwTable> tw_tables;
+    std::map<std::pair<uint32_t, uint64_t>, alb::AutPlan> aut_plans;   // (n, k) -> tile decomposition (aut_plan.hpp)
     // architectural state (persists across run_vp)
     alb::u64 vl = 0, q = 0, iq = 0;
     int mod_idx = -1;

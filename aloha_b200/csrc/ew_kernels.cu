@@ -134,6 +134,74 @@ __global__ void __launch_bounds__(kThreads) autmac_kernel(const AutMacJob *__res
     }
 }
 
+// ---- VAUT through shared-memory tiles (aut_plan.hpp) -----------------------------------------------
+// One CTA = one tile of the (point j, offset f) cover of Z_n.  Load phase: lanes run along j, so a warp
+// reads runs of consecutive SOURCE words; store phase: lanes run along f, so a warp writes runs of
+// consecutive DESTINATION words (and, fused, reads p and c along the same runs).  Both sides of the
+// permutation move in 128-byte lines; the transposition is the padded shared-memory tile.
+// Same per-element function as the gather kernels: raw q - x on the negated half ((i*k) mod 2n >= n).
+constexpr int kAutIters = kAutTile / kThreads;      // 8 slots per thread
+static_assert(kThreads == (int)kAutThreads, "aut_plan.hpp replays the kernels with this block size");
+
+template <bool MAC, class Job>
+__device__ __forceinline__ void aut_tile_body(const Job &job, u32 n, u64 *tile) {
+    const AutPlan &P = job.plan;
+    const AutTile T = aut_tile(P, blockIdx.x);
+    const u32 slots = 1u << (T.log_jb + T.log_fb);
+    const u64 *__restrict__ src;
+    if constexpr (MAC) src = job.x; else src = job.src;
+    // load: slot s = fl * JB + jl
+    u64 v[kAutIters];
+#pragma unroll
+    for (int it = 0; it < kAutIters; ++it) {
+        u32 jl, fl;
+        const u32 s = it * kThreads + threadIdx.x;
+        aut_load_slot(T, s, &jl, &fl);
+        if (s < slots && jl < T.jcount && fl < T.fcount) v[it] = __ldg(src + aut_src(P, T, jl, fl));
+    }
+#pragma unroll
+    for (int it = 0; it < kAutIters; ++it) {
+        u32 jl, fl;
+        const u32 s = it * kThreads + threadIdx.x;
+        aut_load_slot(T, s, &jl, &fl);
+        if (s < slots && jl < T.jcount && fl < T.fcount) tile[fl * T.stride + jl] = v[it];
+    }
+    __syncthreads();
+    // store: slot s = jl * FB + fl
+    const u64 q = job.q, k2 = job.k & (2ull * n - 1);
+#pragma unroll
+    for (int it = 0; it < kAutIters; ++it) {
+        u32 jl, fl;
+        const u32 s = it * kThreads + threadIdx.x;
+        aut_store_slot(T, s, &jl, &fl);
+        if (s < slots && jl < T.jcount && fl < T.fcount) {
+            const u32 i = aut_src(P, T, jl, fl), d = aut_dst(P, T, jl, fl);
+            const u64 x = tile[fl * T.stride + jl];
+            const bool neg = (((u64)i * k2) & (2ull * n - 1)) >= n;
+            const u64 y = neg ? q - x : x;
+            if constexpr (MAC) {
+                const u64 m = rtl_alu<ALU_MUL_VV>(y, job.p[d], 0, q, job.iq);
+                job.dst[d] = rtl_alu<ALU_ADD_VV>(job.c[d], m, 0, q, job.iq);
+            } else {
+                job.dst[d] = y;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) vaut_tiled_kernel(const AutJob *__restrict__ jobs, u32 n) {
+    __shared__ u64 tile[kAutSmemWords];
+    const AutJob &job = jobs[blockIdx.y];
+    if (blockIdx.x >= job.plan.ntiles) return;
+    aut_tile_body<false>(job, n, tile);
+}
+__global__ void __launch_bounds__(kThreads) autmac_tiled_kernel(const AutMacJob *__restrict__ jobs, u32 n) {
+    __shared__ u64 tile[kAutSmemWords];
+    const AutMacJob &job = jobs[blockIdx.y];
+    if (blockIdx.x >= job.plan.ntiles) return;
+    aut_tile_body<true>(job, n, tile);
+}
+
 // dst = c + a*b : product and sum exactly as VFQMUL.vv then VFQADD.vv would store them
 __global__ void __launch_bounds__(kThreads) muladd_kernel(const MulAddJob *__restrict__ jobs, u32 n) {
     const MulAddJob job = jobs[blockIdx.y];
@@ -237,6 +305,16 @@ cudaError_t launch_ew(u32 op, const EwJob *jobs, u32 njobs, u32 n, cudaStream_t 
 
 cudaError_t launch_vaut(const PermJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
     vaut_kernel<<<grid_for(n, njobs), kThreads, 0, st>>>(jobs, n);
+    ++g_launches;
+    return cudaGetLastError();
+}
+cudaError_t launch_vaut_tiled(const AutJob *jobs, u32 njobs, u32 n, u32 max_tiles, cudaStream_t st) {
+    vaut_tiled_kernel<<<dim3(max_tiles, njobs), kThreads, 0, st>>>(jobs, n);
+    ++g_launches;
+    return cudaGetLastError();
+}
+cudaError_t launch_autmac_tiled(const AutMacJob *jobs, u32 njobs, u32 n, u32 max_tiles, cudaStream_t st) {
+    autmac_tiled_kernel<<<dim3(max_tiles, njobs), kThreads, 0, st>>>(jobs, n);
     ++g_launches;
     return cudaGetLastError();
 }

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "aut_plan.hpp"
+
 namespace alb {
 
 typedef unsigned long long u64;
@@ -75,6 +77,16 @@ struct PermJob {
     u64 kinv;              // VAUT: k^-1 mod n (gather form); VROLI: rot mod n
 };
 
+// VAUT through the tile decomposition of aut_plan.hpp (the default path; PermJob + vaut_kernel is the
+// 8-byte gather kept for A/B measurements, ALOHA_F_AUT_GATHER).
+struct AutJob {
+    u64 *dst;
+    const u64 *src;
+    u64 q;
+    u64 k;                 // Galois element as the RTL sees it: the sign comes from (i*k) mod 2n
+    AutPlan plan;
+};
+
 // One stage of the reference's constant-geometry schedule, word-exact (ALOHA_F_STRICT):
 //   forward  : dst[2p] = add(r(x[p]), m), dst[2p+1] = sub(r(x[p]), m), m = barrett(r(x[p+N/2]), w), w = tw[2^s + (p mod 2^s)]
 //   inverse  : dst[p] = half(add(x[2p], x[2p+1])), dst[p+N/2] = half(barrett(sub(x[2p], x[2p+1]), w)), w = itw[2^f + (p mod 2^f)], f = logN-1-s
@@ -122,6 +134,7 @@ struct AutMacJob {
     const u64 *x;
     const u64 *p;
     u64 q, iq, k, kinv;
+    AutPlan plan;          // tile decomposition of (n, k) (aut_plan.hpp); unused by the gather variant
 };
 
 // The forward row pass's layout of the same 256-entry block (a whole warp per row, 8 coefficients per
@@ -166,7 +179,10 @@ cudaError_t launch_ntt_forward(const NttJob *jobs_dev, u32 njobs, const NttRowGr
 cudaError_t launch_ntt_inverse(const NttJob *jobs_dev, u32 njobs, const NttRowGroup *groups_dev, u32 ngroups,
                                const TmaMaps *maps_host, u32 logn, u32 form, cudaStream_t st);
 cudaError_t launch_ew(u32 alu_op, const EwJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
-cudaError_t launch_vaut(const PermJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
+cudaError_t launch_vaut(const PermJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);          // 8-byte gather
+// tiled: max_tiles = the largest plan.ntiles among the launch's jobs
+cudaError_t launch_vaut_tiled(const AutJob *jobs_dev, u32 njobs, u32 n, u32 max_tiles, cudaStream_t st);
+cudaError_t launch_autmac_tiled(const AutMacJob *jobs_dev, u32 njobs, u32 n, u32 max_tiles, cudaStream_t st);
 cudaError_t launch_vroli(const PermJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
 cudaError_t launch_pease(const PeaseJob *jobs_dev, u32 njobs, u32 logn, u32 stage, bool inverse, cudaStream_t st);
 cudaError_t launch_copy(const CopyJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);

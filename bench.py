@@ -213,8 +213,10 @@ def run_gpu(args):
             out = measure_keyswitch(torch, dist, A, {"device": local}, stream, timed0, world, rank)
         elif args.only == "tv":
             out = measure_tv_latency(A) if rank == 0 else None
+        elif args.only == "rotmac_gather":
+            out = measure_rotmac(torch, A, asm, {"device": local}, primes, psis, stream, timed0, args.polys, flags=A.F_AUT_GATHER)
         else:
-            out = measure_rotmac(torch, A, asm, {"device": local}, primes, psis, stream, timed0, 16)
+            out = measure_rotmac(torch, A, asm, {"device": local}, primes, psis, stream, timed0, args.polys)
         if rank == 0:
             print(json.dumps(out), flush=True)
         if world > 1:
@@ -322,7 +324,7 @@ def run_gpu(args):
     if not args.no_extra:
         eng_kwargs = {"device": local}
         if world == 1:
-            extra["rotate_mac"] = measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, 16)
+            extra["automorphism"] = measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, POLYS)
             extra["tv_latency"] = measure_tv_latency(A)
         extra["keyswitch"] = measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank)
 
@@ -483,33 +485,85 @@ def measure_tv_latency(A):
     return out
 
 
-def measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, polys):
-    """BASELINE.json configs[3]: per limb acc' = acc + aut_k(x) * p, N = 2^16, 32 limbs x `polys`."""
+def galois_elements():
+    """BASELINE.json configs[3]: rotation Galois elements 3^step mod 2N (the reference host's convention,
+    top_noaxilite_tb.sv:531) for steps 1, 2, 8, N/8 (= N/2 + 1: the most skewed lattice there is) and 18, the
+    first step whose element is >= N (102729; k mod N = 37193: a pseudo-random permutation, top bit in the signs)."""
+    ks = [("3^1", pow(3, 1, 2 * N)), ("3^2", pow(3, 2, 2 * N)), ("3^8", pow(3, 8, 2 * N)), ("3^(N/8)", pow(3, N // 8, 2 * N)),
+          ("3^18", pow(3, 18, 2 * N))]
+    assert any(k >= N and k % N != 1 for _, k in ks)
+    return ks
+
+
+def measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, polys, flags=0, quick=False):
+    """BASELINE.json configs[3]: automorphism and rotate-and-sum at N = 2^16, 32 limbs x `polys` polynomials.
+      vaut       : rslt[l] = aut_k(x[l])                 algorithmic bytes 2*N*8 per limb
+      rotate_mac : rslt[l] = acc[l] + aut_k(x[l]) * p[l] algorithmic bytes 4*N*8 per limb (one fused kernel)
+    for every Galois element of galois_elements(); one limb-polynomial per element is checked against the
+    oracle inside the run (cpu_baseline leg).  The engine is built with vlmax = 2N so that k >= N keeps
+    its top bit (on a vlmax = N machine the RTL truncates k to log2 N bits)."""
+    from oracle import oracle as O
+    peak, _ = peaks()
     per_poly = LIMBS * ROWS_PER_POLY
-    eng = A.Engine(vlmax_bits=N * 64, spm_rows=4 * polys * per_poly, ksk_rows=0, moduli=(), pool_buffers=128, **eng_kwargs)
+    eng = A.Engine(vlmax_bits=2 * N * 64, spm_rows=4 * polys * per_poly, ksk_rows=0, moduli=(), pool_buffers=2 * LIMBS + 8,
+                   flags=flags, **eng_kwargs)
     eng.set_stream(stream.cuda_stream)
-    eng.load_isram(asm.rotate_mac_stream(N, primes).words(), 0)
-    x = synth_batch(primes, polys, 7)
-    eng.dma_mem_h2d(0, x.reshape(-1))                                          # x
-    eng.dma_mem_h2d(polys * per_poly, np.concatenate([x, x], axis=1).reshape(-1))   # [p | acc] per poly
-    k = pow(3, N // 4, 2 * N)                                                  # a Galois element >= N
-    calls = A.Engine.make_args([(b * per_poly, polys * per_poly + 2 * b * per_poly, 3 * polys * per_poly + b * per_poly,
-                                 0, k) for b in range(polys)])
-    t0 = time.perf_counter()
-    while time.perf_counter() - t0 < 0.3:
-        eng.run_vp_batch(0, calls)
-        torch.cuda.synchronize()
-    s0 = eng.stats()
-    steps = 20
-    ms = timed(lambda: eng.run_vp_batch(0, calls), steps)
-    s1 = eng.stats()
-    per_s = LIMBS * polys * steps / (ms / 1e3)
+    prog_mac, prog_aut = asm.rotate_mac_stream(N, primes), asm.vaut_stream(N, primes)
+    eng.load_isram(prog_mac.words(), 0)
+    eng.load_isram(prog_aut.words(), 2048)
+    rng = np.random.default_rng(7)
+    qv = np.array(primes, dtype=np.uint64)
+    # 8 distinct polynomials tiled over the batch (host memory: 3 x 128 MiB instead of 3 x 1 GiB)
+    base = [rng.integers(0, 1 << 59, (min(polys, 8), LIMBS, N), dtype=np.uint64) % qv[None, :, None] for _ in range(3)]
+    x, p, acc = base
+    reps = (polys + 7) // 8
+    for r in range(reps):
+        cnt = min(8, polys - 8 * r)
+        eng.dma_mem_h2d(8 * r * per_poly, x[:cnt].reshape(-1))
+        eng.dma_mem_h2d(polys * per_poly + 2 * 8 * r * per_poly, np.concatenate([p[:cnt], acc[:cnt]], axis=1).reshape(-1))
+    out_row = 3 * polys * per_poly
+    steps = 5 if quick else 10
+    res = {"vaut": {}, "rotate_mac": {}}
+    ok = True
+    for name, k in galois_elements():
+        mac_calls = A.Engine.make_args([(b * per_poly, polys * per_poly + 2 * b * per_poly, out_row + b * per_poly, 0, k)
+                                        for b in range(polys)])
+        aut_calls = A.Engine.make_args([(b * per_poly, 0, out_row + b * per_poly, 0, k) for b in range(polys)])
+        for kind, pc, calls, bytes_per in (("vaut", 2048, aut_calls, 2 * N * 8), ("rotate_mac", 0, mac_calls, 4 * N * 8)):
+            for _ in range(3):
+                eng.run_vp_batch(pc, calls)
+            torch.cuda.synchronize()
+            s0 = eng.stats()
+            ms = timed(lambda: eng.run_vp_batch(pc, calls), steps)
+            s1 = eng.stats()
+            per_s = LIMBS * polys * steps / (ms / 1e3)
+            # one limb-polynomial of the last polynomial against the oracle
+            b, l = polys - 1, (k >> 3) % LIMBS
+            got = eng.dma_mem_d2h(out_row + b * per_poly + l * ROWS_PER_POLY, N)
+            if kind == "vaut":
+                want = O.automorph(x[b % 8, l], k, primes[l])
+            else:
+                want = O.aut_mac_batch(acc[b % 8, l:l + 1].copy(), x[b % 8, l:l + 1], p[b % 8, l:l + 1], k, qv[l:l + 1],
+                                       np.zeros(1, dtype=np.uint32))[0]
+            good = bool((got == want).all())
+            ok = ok and good
+            res[kind][name] = {"k": k, "value": per_s, "ms_per_step": ms / steps,
+                               "achieved_gbs_algorithmic": per_s * bytes_per / 1e9,
+                               "frac_of_hbm_peak": per_s * bytes_per / 1e9 / peak,
+                               "launches_per_step": (s1["kernel_launches"] - s0["kernel_launches"]) / steps,
+                               "checked_against_oracle": good}
     eng.close()
-    return {"value": per_s, "unit": "limb rotate-MACs/s", "ms_per_step": ms / steps, "galois_k": k,
-            "launches_per_step": (s1["kernel_launches"] - s0["kernel_launches"]) / steps,
-            "ops_fused_per_step": (s1["ops_fused"] - s0["ops_fused"]) / steps,
-            "algorithmic_bytes_per_unit": 4 * N * 8,
-            "achieved_gbs_algorithmic": per_s * 4 * N * 8 / 1e9}
+    out = {"polys": polys, "limbs": LIMBS, "n": N, "kernel": "gather (ALOHA_F_AUT_GATHER)" if flags & A.F_AUT_GATHER else
+           "shared-memory tile permutation (aut_plan.hpp)", "all_checked_against_oracle": ok}
+    for kind, bytes_per, unit in (("vaut", 2 * N * 8, "limb automorphisms/s"), ("rotate_mac", 4 * N * 8, "limb rotate-MACs/s")):
+        vals = [v["value"] for v in res[kind].values()]
+        worst = min(vals)
+        out[kind] = {"value": worst, "unit": unit, "value_is": "the slowest Galois element", "mean": float(np.mean(vals)),
+                     "algorithmic_bytes_per_unit": bytes_per,
+                     "roofline": {"bound": "hbm", "achieved": worst * bytes_per / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": worst * bytes_per / 1e9 / peak},
+                     "per_galois_element": res[kind]}
+    return out
 
 
 def measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank, L=47):
@@ -603,7 +657,7 @@ def main():
     ap.add_argument("--chunk-mib", type=int, default=0, help="override the engine's L2 chunk size")
     ap.add_argument("--polys", type=int, default=64)
     ap.add_argument("--no-extra", action="store_true", help="skip the rotate-MAC and key-switch workloads")
-    ap.add_argument("--only", default="", choices=["", "keyswitch", "rotmac", "tv"], help="profiling: run one extra workload alone")
+    ap.add_argument("--only", default="", choices=["", "keyswitch", "rotmac", "rotmac_gather", "tv"], help="profiling: run one extra workload alone")
     args = ap.parse_args()
     globals()["POLYS"] = args.polys
     if args.impl == "reference":

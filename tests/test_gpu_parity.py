@@ -16,7 +16,8 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
-FLAG_SETS = [0, A.F_NO_BATCH, A.F_NO_ALIAS, A.F_NO_BATCH | A.F_NO_ALIAS, A.F_GRAPHS, A.F_NO_FUSE, A.F_STRICT, A.F_DEFER]
+FLAG_SETS = [0, A.F_NO_BATCH, A.F_NO_ALIAS, A.F_NO_BATCH | A.F_NO_ALIAS, A.F_GRAPHS, A.F_NO_FUSE, A.F_STRICT, A.F_DEFER,
+             A.F_AUT_GATHER]
 
 
 def tv_engine(flags=0):
@@ -281,6 +282,91 @@ def test_rotate_mac_stream_vs_oracle():
     # the batcher folds VAUT + VFQMUL + VFQADD of every limb but the last (whose temporaries stay
     # architecturally visible in v2 / v4) into the gather-multiply-add kernel
     assert eng.stats()["ops_fused"] == 2 * (L - 1)
+
+
+@pytest.mark.parametrize("flags", [0, A.F_AUT_GATHER])
+@pytest.mark.parametrize("n", [256, 2048, 65536])
+def test_vaut_every_kind_of_galois_element(n, flags):
+    """The tiled permutation (aut_plan.hpp) and the 8-byte gather against the oracle for Galois elements
+    whose lattices are balanced, extremely skewed (3, N/2+1, 1/3 mod N), the reversal 2N-1 and the identity
+    permutation N+1 -- several in ONE launch, so tile counts differ between the launch's jobs."""
+    rp = n // 128
+    q = O.Q0
+    rng = np.random.default_rng(n + flags)
+    ks = [3, 9, pow(3, 8, 2 * n), pow(3, n // 8, 2 * n), 2 * n - 1, n + 1, n // 2 + 1, pow(3, -1, n), 12345 | 1, n - 3]
+    x = rng.integers(0, q, (len(ks), n), dtype=np.uint64)
+    x[:, :3] = 0
+    eng = A.Engine(vlmax_bits=2 * n * 64, spm_rows=2 * len(ks) * rp, ksk_rows=0, moduli=(), flags=flags)
+    eng.load_isram(asm.Program().vsetvl(n).vsetq(q).vle(0, 0, 0).vaut(2, 0).vse(2, 2, 0).brk().words(), 0)
+    eng.dma_mem_h2d(0, x.reshape(-1))
+    eng.run_vp_batch(0, [(i * rp, 0, (len(ks) + i) * rp, 0, k) for i, k in enumerate(ks)])
+    got = eng.dma_mem_d2h(len(ks) * rp, len(ks) * n).reshape(len(ks), n)
+    for i, k in enumerate(ks):
+        assert (got[i] == O.automorph(x[i], k & (2 * n - 1), q)).all(), (n, k)
+    assert eng.stats()["kernel_launches"] == 1
+
+
+@pytest.mark.parametrize("flags", [0, A.F_AUT_GATHER])
+def test_rotate_mac_full_size_vs_oracle(flags):
+    """BASELINE.json configs[3] at its real size: N = 2^16, 32 limbs, fused aut-mul-add, every word of two
+    polynomials' worth of limbs against the oracle, for a small, a pseudo-random and a >= N Galois element."""
+    n, L, B = 65536, 32, 2
+    rp = n // 128
+    primes, psis = synth(n, L)
+    qv = np.array(primes, dtype=np.uint64)
+    per_poly = L * rp
+    eng = A.Engine(vlmax_bits=n * 64, spm_rows=4 * B * per_poly, ksk_rows=0, moduli=(), pool_buffers=160, flags=flags)
+    eng.load_isram(asm.rotate_mac_stream(n, primes).words(), 0)
+    rng = np.random.default_rng(11)
+    x, p, acc = (rng.integers(0, 1 << 59, (B, L, n), dtype=np.uint64) % qv[None, :, None] for _ in range(3))
+    eng.dma_mem_h2d(0, x.reshape(-1))
+    eng.dma_mem_h2d(B * per_poly, np.concatenate([p, acc], axis=1).reshape(-1))
+    for step in (1, n // 8, 1000):
+        k = pow(3, step, 2 * n)
+        if step == 1000:
+            k |= n                                      # a Galois element >= N with k mod N != 1 (SURVEY Q5 truncation)
+        eng.run_vp_batch(0, [(b * per_poly, B * per_poly + 2 * b * per_poly, 3 * B * per_poly + b * per_poly, 0, k)
+                             for b in range(B)])
+        got = eng.dma_mem_d2h(3 * B * per_poly, B * L * n).reshape(B, L, n)
+        k_seen = k & (n - 1)                            # vlmax/64 = n: the RTL keeps log2(n) bits of k
+        for b in range(B):
+            want = O.aut_mac_batch(acc[b].copy(), x[b], p[b], k_seen, qv, np.arange(L), nthreads=8)
+            assert (got[b] == want).all(), (step, b)
+    assert eng.stats()["ops_fused"] > 0
+
+
+def test_fusion_keeps_in_place_rotate_accumulate_exact():
+    """VLE v1 <- M; VAUT; (v1 redefined); MUL; ADD; VSE -> M in a batch of calls.  The fused
+    gather-multiply-add must not read x from the range it writes."""
+    n, L = 4096, 1
+    rp = n // 128
+    q = synth(n, 1)[0][0]
+    calls = 3
+    prog = (asm.Program().vsetvl(n).vsetq(q)
+            .vle(1, 0, 0).vaut(2, 1)                    # v2 = aut(M)
+            .vle(1, 1, 0)                               # v1 redefined: the alias of M is gone
+            .vfqmul(4, 2, 1).vle(3, 1, rp).vfqadd(6, 4, 3)
+            .vse(6, 0, 0).brk())                        # result back into M
+    rng = np.random.default_rng(4)
+    m0 = rng.integers(0, q, (calls, n), dtype=np.uint64)
+    pa = rng.integers(0, q, (2, n), dtype=np.uint64)
+    k = pow(3, 5, 2 * n)
+    outs = []
+    for flags in (0, A.F_NO_FUSE | A.F_NO_BATCH, A.F_AUT_GATHER):
+        eng = A.Engine(vlmax_bits=n * 64, spm_rows=(calls + 2) * rp, ksk_rows=0, moduli=(), flags=flags, pool_buffers=34)
+        eng.load_isram(prog.words(), 0)
+        eng.dma_mem_h2d(0, m0.reshape(-1))
+        eng.dma_mem_h2d(calls * rp, pa.reshape(-1))
+        for _ in range(2):                              # second round: temporaries of the first are dead
+            eng.run_vp_batch(0, [(c * rp, calls * rp, 0, 0, k) for c in range(calls)])
+        outs.append(eng.dma_mem_d2h(0, calls * n))
+    qv = np.array([q], dtype=np.uint64)
+    want = m0.copy()
+    for _ in range(2):
+        for c in range(calls):
+            want[c] = O.aut_mac_batch(pa[1:2].copy(), want[c:c + 1], pa[0:1], k & (n - 1), qv, np.zeros(1, dtype=np.int64))[0]
+    for o in outs:
+        assert (o.reshape(calls, n) == want).all()
 
 
 # ------------------------------------------------------------------ batcher / architectural state
