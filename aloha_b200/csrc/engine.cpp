@@ -21,6 +21,19 @@ namespace {
         }                                                                               \
     } while (0)
 
+// Every entry point runs with the engine's device current and puts the caller's device back on exit: a
+// caller may drive several engines (one per GPU) from one thread, or switch devices between calls.
+struct DeviceGuard {
+    int prev = -1, dev;
+    explicit DeviceGuard(int d) : dev(d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 int fail(aloha *E, int code, const std::string &msg) {
     E->last_error = msg;
     return code;
@@ -1143,7 +1156,7 @@ int aloha_create(const aloha_cfg *cfg, aloha_t **out) {
         E->last_error = "no CUDA device " + std::to_string(cfg->device) + " (this engine has no CPU fallback)";
         return ALOHA_E_CUDA;
     }
-    CU(cudaSetDevice(cfg->device));
+    DeviceGuard dg_(cfg->device);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10) {
@@ -1171,6 +1184,7 @@ int aloha_create(const aloha_cfg *cfg, aloha_t **out) {
 
 void aloha_destroy(aloha_t *E) {
     if (!E) return;
+    DeviceGuard dg_(E->device);
     if (E->own_stream) cudaStreamSynchronize(E->own_stream);
     free_plans(E);
     free_tables(E);
@@ -1186,6 +1200,7 @@ void aloha_destroy(aloha_t *E) {
 
 int aloha_load_isram(aloha_t *E, const uint8_t *words, uint32_t n, uint32_t at_pc) {
     if (!E || !words) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     FLUSH();
     if ((u64)at_pc + n > E->iram_depth) return fail(E, ALOHA_E_RANGE, "beyond the instruction ROM (cfg.isram_depth)");
     std::memcpy(&E->isram[(size_t)at_pc * 12], words, (size_t)n * 12);
@@ -1195,9 +1210,11 @@ int aloha_load_isram(aloha_t *E, const uint8_t *words, uint32_t n, uint32_t at_p
 
 int aloha_load_tf_rom(aloha_t *E, const uint64_t *q, const uint64_t *psi, uint32_t n) {
     if (!E || !q || !psi) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     FLUSH();
     CU(cudaStreamSynchronize(E->stream));
     free_tables(E);
+    free_plans(E);          // they point into the tables just freed
     E->mod_q.assign(q, q + n);
     E->mod_psi.assign(psi, psi + n);
     ++E->tf_version;
@@ -1209,6 +1226,7 @@ int aloha_load_tf_rom(aloha_t *E, const uint64_t *q, const uint64_t *psi, uint32
 
 int aloha_dma_mem_h2d(aloha_t *E, uint32_t row, const uint64_t *src, uint64_t bytes) {
     if (!E || !src || bytes % 64) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     FLUSH();
     const u64 off = (u64)row * kLanes, n = bytes / 8;
     if (off + n > E->spm_words) return fail(E, ALOHA_E_RANGE, "DMA beyond SPM");
@@ -1222,6 +1240,7 @@ int aloha_dma_mem_h2d(aloha_t *E, uint32_t row, const uint64_t *src, uint64_t by
 
 int aloha_dma_mem_h2d_async(aloha_t *E, uint32_t row, const uint64_t *src, uint64_t bytes) {
     if (!E || !src || bytes % 64) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     FLUSH();
     const u64 off = (u64)row * kLanes, n = bytes / 8;
     if (off + n > E->spm_words) return fail(E, ALOHA_E_RANGE, "DMA beyond SPM");
@@ -1252,6 +1271,7 @@ int aloha_dma_mem_h2d_async(aloha_t *E, uint32_t row, const uint64_t *src, uint6
 
 int aloha_dma_mem_d2h_async(aloha_t *E, uint64_t *dst, uint32_t row, uint64_t bytes) {
     if (!E || !dst || bytes % 64) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     FLUSH();
     const u64 off = (u64)row * kLanes, n = bytes / 8;
     if (off + n > E->spm_words) return fail(E, ALOHA_E_RANGE, "DMA beyond SPM");
@@ -1276,6 +1296,7 @@ int aloha_dma_mem_d2h_async(aloha_t *E, uint64_t *dst, uint32_t row, uint64_t by
 
 int aloha_dma_mem_d2h(aloha_t *E, uint64_t *dst, uint32_t row, uint64_t bytes) {
     if (!E || !dst || bytes % 64) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     FLUSH();
     const u64 off = (u64)row * kLanes, n = bytes / 8;
     if (off + n > E->spm_words) return fail(E, ALOHA_E_RANGE, "DMA beyond SPM");
@@ -1286,6 +1307,7 @@ int aloha_dma_mem_d2h(aloha_t *E, uint64_t *dst, uint32_t row, uint64_t bytes) {
 
 int aloha_dma_ksk_h2d(aloha_t *E, uint32_t row, const uint64_t *src, uint64_t bytes) {
     if (!E || !src || bytes % 64) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     FLUSH();
     const u64 off = (u64)row * kLanes, n = bytes / 8;
     if (off + n > E->ksk_words) return fail(E, ALOHA_E_RANGE, "DMA beyond KSK memory");
@@ -1310,6 +1332,7 @@ int aloha_dma_ksk_h2d(aloha_t *E, uint32_t row, const uint64_t *src, uint64_t by
 
 int aloha_spm_written(aloha_t *E, uint32_t row, uint64_t nwords, uint8_t *out) {
     if (!E || !out) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     FLUSH();
     const u64 off = (u64)row * kLanes;
     if (off + nwords > E->spm_words) return fail(E, ALOHA_E_RANGE, "range beyond SPM");
@@ -1320,22 +1343,26 @@ int aloha_spm_written(aloha_t *E, uint32_t row, uint64_t nwords, uint8_t *out) {
 int aloha_run_vp(aloha_t *E, uint32_t pc, uint32_t src0, uint32_t src1, uint32_t rslt, uint32_t ksk_ptr,
                  uint32_t step) {
     if (!E) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     const aloha_vp_args a{src0, src1, rslt, ksk_ptr, step};
     return enqueue_or_run(E, &pc, true, 1, &a);
 }
 
 int aloha_run_vp_batch(aloha_t *E, uint32_t pc, uint32_t count, const aloha_vp_args *args) {
     if (!E || (count && !args)) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     return enqueue_or_run(E, &pc, true, count, args);
 }
 
 int aloha_run_vp_multi(aloha_t *E, uint32_t count, const uint32_t *pcs, const aloha_vp_args *args) {
     if (!E || (count && (!args || !pcs))) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     return enqueue_or_run(E, pcs, false, count, args);
 }
 
 int aloha_sync(aloha_t *E) {
     if (!E) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     FLUSH();
     CU(cudaStreamSynchronize(E->stream));
     if (E->up_stream) {
@@ -1349,6 +1376,7 @@ int aloha_sync(aloha_t *E) {
 
 int aloha_spm_device_ptr(aloha_t *E, uint32_t row, void **p) {
     if (!E || !p) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     FLUSH();
     if (row >= E->cfg.spm_rows) return fail(E, ALOHA_E_RANGE, "row beyond SPM");
     *p = E->d_spm + (u64)row * kLanes;
@@ -1356,6 +1384,7 @@ int aloha_spm_device_ptr(aloha_t *E, uint32_t row, void **p) {
 }
 int aloha_ksk_device_ptr(aloha_t *E, uint32_t row, void **p) {
     if (!E || !p) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     FLUSH();
     if (row >= E->cfg.ksk_rows) return fail(E, ALOHA_E_RANGE, "row beyond KSK memory");
     *p = E->d_ksk + (u64)row * kLanes;
@@ -1363,6 +1392,7 @@ int aloha_ksk_device_ptr(aloha_t *E, uint32_t row, void **p) {
 }
 int aloha_spm_mark_written(aloha_t *E, uint32_t row, uint32_t nrows) {
     if (!E) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     FLUSH();
     if ((u64)row + nrows > E->cfg.spm_rows) return fail(E, ALOHA_E_RANGE, "rows beyond SPM");
     int rc = cow_for_host_write(E, (u64)row * kLanes, (u64)nrows * kLanes);
@@ -1372,6 +1402,7 @@ int aloha_spm_mark_written(aloha_t *E, uint32_t row, uint32_t nrows) {
 }
 int aloha_set_stream(aloha_t *E, void *stream) {
     if (!E) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
     FLUSH();
     CU(cudaStreamSynchronize(E->stream));
     E->stream = stream ? (cudaStream_t)stream : E->own_stream;
@@ -1381,6 +1412,7 @@ int aloha_set_stream(aloha_t *E, void *stream) {
 int aloha_get_stats(const aloha_t *Ec, aloha_stats *out) {
     if (!Ec || !out) return ALOHA_E_ARG;
     aloha_t *E = const_cast<aloha_t *>(Ec);   // logically const: queued calls are part of the observable state
+    DeviceGuard dg_(E->device);
     FLUSH();
     *out = E->stats;
     return ALOHA_OK;
@@ -1388,6 +1420,7 @@ int aloha_get_stats(const aloha_t *Ec, aloha_stats *out) {
 int aloha_get_csr(const aloha_t *Ec, uint64_t *vl, uint64_t *q, uint64_t *iq) {
     if (!Ec) return ALOHA_E_ARG;
     aloha_t *E = const_cast<aloha_t *>(Ec);
+    DeviceGuard dg_(E->device);
     FLUSH();
     if (vl) *vl = E->vl;
     if (q) *q = E->q;

@@ -8,12 +8,14 @@
 //                                                            cannot alias the access away)
 // All of them are HBM-bound streams: 16-byte vector accesses, one job table per launch
 // (blockIdx.y = job), grids sized so every SM holds several CTAs.
+#include <atomic>
+
 #include "kernels.cuh"
 #include "modarith.cuh"
 
 namespace alb {
 
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;
 
 namespace {
 

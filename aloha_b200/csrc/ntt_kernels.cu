@@ -33,6 +33,7 @@
 // ntt_inv_rows_tma) for batches that hold runs of 16 polynomials under one modulus -- rows, the row's
 // twiddle block and the group record are staged in shared memory by cp.async.bulk / cp.async.bulk.tensor
 // behind mbarriers, one tile ahead of the butterflies.
+#include <atomic>
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -715,17 +716,21 @@ __global__ void __launch_bounds__(256, COLS_MINB) ntt_inv_cols(const NttJob *__r
 }
 
 // ============================================================================ launchers
-unsigned long long g_launches = 0;
-unsigned long long kernel_launch_count() { return g_launches; }
-static inline void count_launch() { ++g_launches; }
+std::atomic<unsigned long long> g_launches{0};
+unsigned long long kernel_launch_count() { return g_launches.load(std::memory_order_relaxed); }
+static inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// SM count of the CURRENT device (engines on different GPUs may share this process)
 static int sm_count() {
-    static int n = 0;
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    int n = cache[dev].load(std::memory_order_relaxed);
     if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
     }
     return n;
 }
@@ -740,7 +745,10 @@ static cudaError_t fwd_impl(const NttJob *jobs, u32 njobs, const NttRowGroup *gr
         count_launch();
     }
     if (ngroups) {
-        static int resident = 0;            // CTAs of the persistent row pass that fit on one SM
+        static int resident_dev[64] = {};   // CTAs of the persistent row pass that fit on one SM (function
+        int dev = 0;                        // attributes are per device: set them on each one the process uses)
+        cudaGetDevice(&dev);
+        int &resident = resident_dev[dev & 63];
         if (!resident) {
             cudaError_t e = cudaFuncSetAttribute(ntt_fwd_rows_tma<S1, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdRowsSmem));
             if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ntt_fwd_rows_tma<S1, FORM>, 32 * kTileRows8, sizeof(FwdRowsSmem));
@@ -765,7 +773,10 @@ static cudaError_t inv_impl(const NttJob *jobs, u32 njobs, const NttRowGroup *gr
     constexpr int R = 1 << S1;
     if (ngroups) {
         constexpr size_t kSmem = sizeof(InvRowsSmem) + 1024;
-        static int resident = 0;
+        static int resident_dev[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        int &resident = resident_dev[dev & 63];
         if (!resident) {
             cudaError_t e = cudaFuncSetAttribute(ntt_inv_rows_tma<S1, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
             if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ntt_inv_rows_tma<S1, FORM>, 16 * kTileRows, kSmem);

@@ -146,6 +146,22 @@ class TorchComm:
         self.dist, self.group = dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
 
+    def _bind(self, machine):
+        """The collectives below run on a torch stream, directly on SPM device memory: the engine must launch
+        on that same stream or its kernels race with them (the engine's default is a private non-blocking
+        stream).  Returns the stream to run the collective on: torch's current one, or -- when that is the
+        legacy default stream, whose handle 0 would select the engine's own -- a stream this object owns."""
+        import torch
+        cur = torch.cuda.current_stream()
+        if cur.cuda_stream == 0:
+            if getattr(self, "_own_stream", None) is None:
+                self._own_stream = torch.cuda.Stream()
+            cur = self._own_stream
+        if hasattr(machine, "set_stream") and getattr(machine, "_bound_stream", None) != cur.cuda_stream:
+            machine.set_stream(cur.cuda_stream)
+            machine._bound_stream = cur.cuda_stream
+        return cur
+
     def _spm_tensor(self, machine, row, nrows):
         import torch
 
@@ -161,10 +177,12 @@ class TorchComm:
         lay, m = ks.lay, ks.machine
         block = lay.per_rank * lay.rp
         if hasattr(m, "spm_device_ptr"):
+            st = self._bind(m)
             m.spm_mark_written(lay.S, lay.slots * lay.rp)      # copy-on-write for aliased registers
             full = self._spm_tensor(m, lay.S, lay.slots * lay.rp)
             mine = full[self.rank * block * 128:(self.rank + 1) * block * 128]
-            self.dist.all_gather_into_tensor(full, mine, group=self.group)
+            with torch.cuda.stream(st):
+                self.dist.all_gather_into_tensor(full, mine, group=self.group)
         else:
             mine = torch.from_numpy(m.dma_mem_d2h(lay.S + self.rank * block, block * 128).view(np.int64))
             parts = [torch.empty_like(mine) for _ in range(self.world)]
@@ -176,8 +194,10 @@ class TorchComm:
         lay, m = ks.lay, ks.machine
         row, nrows, src = lay.ACC + 2 * lay.L * lay.rp, 2 * lay.rp, lay.owner(lay.L)
         if hasattr(m, "spm_device_ptr"):
+            st = self._bind(m)
             m.spm_mark_written(row, nrows)
-            self.dist.broadcast(self._spm_tensor(m, row, nrows), src=src, group=self.group)
+            with torch.cuda.stream(st):
+                self.dist.broadcast(self._spm_tensor(m, row, nrows), src=src, group=self.group)
         else:
             t = torch.from_numpy(m.dma_mem_d2h(row, nrows * 128).view(np.int64).copy())
             self.dist.broadcast(t, src=src, group=self.group)

@@ -214,9 +214,11 @@ def run_gpu(args):
         elif args.only == "tv":
             out = measure_tv_latency(A) if rank == 0 else None
         elif args.only == "rotmac_gather":
-            out = measure_rotmac(torch, A, asm, {"device": local}, primes, psis, stream, timed0, args.polys, flags=A.F_AUT_GATHER)
+            out = measure_rotmac(torch, A, asm, {"device": local}, primes, psis, stream, timed0, args.polys, flags=A.F_AUT_GATHER,
+                                 quick=args.quick, only_k=args.galois)
         else:
-            out = measure_rotmac(torch, A, asm, {"device": local}, primes, psis, stream, timed0, args.polys)
+            out = measure_rotmac(torch, A, asm, {"device": local}, primes, psis, stream, timed0, args.polys, quick=args.quick,
+                                 only_k=args.galois)
         if rank == 0:
             print(json.dumps(out), flush=True)
         if world > 1:
@@ -495,7 +497,7 @@ def galois_elements():
     return ks
 
 
-def measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, polys, flags=0, quick=False):
+def measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, polys, flags=0, quick=False, only_k=""):
     """BASELINE.json configs[3]: automorphism and rotate-and-sum at N = 2^16, 32 limbs x `polys` polynomials.
       vaut       : rslt[l] = aut_k(x[l])                 algorithmic bytes 2*N*8 per limb
       rotate_mac : rslt[l] = acc[l] + aut_k(x[l]) * p[l] algorithmic bytes 4*N*8 per limb (one fused kernel)
@@ -526,6 +528,8 @@ def measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, polys
     res = {"vaut": {}, "rotate_mac": {}}
     ok = True
     for name, k in galois_elements():
+        if only_k and name != only_k:
+            continue
         mac_calls = A.Engine.make_args([(b * per_poly, polys * per_poly + 2 * b * per_poly, out_row + b * per_poly, 0, k)
                                         for b in range(polys)])
         aut_calls = A.Engine.make_args([(b * per_poly, 0, out_row + b * per_poly, 0, k) for b in range(polys)])
@@ -657,6 +661,7 @@ def main():
     ap.add_argument("--chunk-mib", type=int, default=0, help="override the engine's L2 chunk size")
     ap.add_argument("--polys", type=int, default=64)
     ap.add_argument("--no-extra", action="store_true", help="skip the rotate-MAC and key-switch workloads")
+    ap.add_argument("--galois", default="", help="with --only rotmac: one Galois element by name, e.g. 3^18")
     ap.add_argument("--only", default="", choices=["", "keyswitch", "rotmac", "rotmac_gather", "tv"], help="profiling: run one extra workload alone")
     args = ap.parse_args()
     globals()["POLYS"] = args.polys
