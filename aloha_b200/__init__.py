@@ -17,7 +17,7 @@ import numpy as np
 
 from . import build as _build
 
-__all__ = ["Engine", "HostDriver", "AlohaError", "load_library", "decode", "REFERENCE_MODULI",
+__all__ = ["Engine", "Group", "HostDriver", "AlohaError", "load_library", "decode", "REFERENCE_MODULI",
            "LANES", "VLMAX_BITS", "SPM_ROWS", "KSK_ROWS"]
 
 LANES = 128
@@ -65,7 +65,10 @@ EXPORTS = ["aloha_create", "aloha_destroy", "aloha_strerror", "aloha_last_error"
            "aloha_spm_device_ptr", "aloha_ksk_device_ptr", "aloha_spm_mark_written", "aloha_set_stream",
            "aloha_get_stats", "aloha_get_csr", "aloha_decode", "aloha_host_create",
            "aloha_host_destroy", "aloha_host_num_ops", "aloha_host_dram_write", "aloha_host_dram_read",
-           "aloha_host_set_encoder_output", "aloha_host_run_op", "aloha_write_dump_text"]
+           "aloha_host_set_encoder_output", "aloha_host_run_op", "aloha_write_dump_text",
+           "aloha_flush", "aloha_group_unique_id", "aloha_group_create", "aloha_group_create_local",
+           "aloha_group_destroy", "aloha_group_size", "aloha_group_rank", "aloha_group_last_error",
+           "aloha_group_all_gather_rows", "aloha_group_broadcast_rows", "aloha_group_wait"]
 
 _lib = None
 
@@ -116,6 +119,17 @@ def load_library(rebuild: bool = False) -> C.CDLL:
         "aloha_host_set_encoder_output": (C.c_int, [vp, u32, p64, u64]),
         "aloha_host_run_op": (C.c_int, [vp, u32, p64, p8, p64, p8, C.POINTER(C.c_int)]),
         "aloha_write_dump_text": (C.c_int, [C.c_char_p, p64, p8, u64]),
+        "aloha_flush": (C.c_int, [vp]),
+        "aloha_group_unique_id": (C.c_int, [p8]),
+        "aloha_group_create": (C.c_int, [vp, p8, C.c_int, C.c_int, C.POINTER(vp)]),
+        "aloha_group_create_local": (C.c_int, [C.POINTER(vp), C.c_int, C.POINTER(vp)]),
+        "aloha_group_destroy": (None, [vp]),
+        "aloha_group_size": (C.c_int, [vp]),
+        "aloha_group_rank": (C.c_int, [vp]),
+        "aloha_group_last_error": (C.c_char_p, [vp]),
+        "aloha_group_all_gather_rows": (C.c_int, [vp, u32, u32, u32, u32, u32]),
+        "aloha_group_broadcast_rows": (C.c_int, [vp, u32, u32, C.c_int]),
+        "aloha_group_wait": (C.c_int, [vp, C.c_int]),
     }
     assert sorted(sig) == sorted(EXPORTS)
     for name, (res, args) in sig.items():
@@ -246,6 +260,9 @@ class Engine:
     def sync(self):
         self._ck(self.L.aloha_sync(self.h), "sync")
 
+    def flush(self):
+        self._ck(self.L.aloha_flush(self.h), "flush")
+
     # ---- device-side access
     def spm_device_ptr(self, spm_row: int) -> int:
         p = C.c_void_p()
@@ -272,6 +289,80 @@ class Engine:
         vl, q, iq = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._ck(self.L.aloha_get_csr(self.h, C.byref(vl), C.byref(q), C.byref(iq)), "get_csr")
         return vl.value, q.value, iq.value
+
+
+GROUP_CHUNKED, GROUP_ALL, GROUP_BCAST = 1, -1, -2
+
+
+class Group:
+    """Several engines (one per GPU) as one limb-sharded machine: NCCL transfers between their SPMs, inside
+    the C library (aloha_group_*).  Group.create(engine, id, rank, nranks) for one process per GPU -- the
+    128-byte id comes from Group.unique_id() on rank 0 and travels by whatever channel the ranks share --
+    or Group.local([engines...]) for one process driving several GPUs."""
+
+    def __init__(self, handle, lib, engines):
+        self.h, self.L, self.engines = handle, lib, engines
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        L = load_library()
+        rc = L.aloha_group_unique_id(buf)
+        if rc:
+            raise AlohaError(rc, "group_unique_id", L.aloha_group_last_error(None).decode())
+        return bytes(buf)
+
+    @classmethod
+    def create(cls, engine: Engine, uid: bytes, rank: int, nranks: int) -> "Group":
+        L, h = engine.L, C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        rc = L.aloha_group_create(engine.h, buf, rank, nranks, C.byref(h))
+        if rc:
+            detail = L.aloha_group_last_error(h).decode() if h else ""
+            if h:
+                L.aloha_group_destroy(h)
+            raise AlohaError(rc, "group_create", detail)
+        return cls(h, L, [engine])
+
+    @classmethod
+    def local(cls, engines) -> "Group":
+        engines = list(engines)
+        L, h = engines[0].L, C.c_void_p()
+        arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+        rc = L.aloha_group_create_local(arr, len(engines), C.byref(h))
+        if rc:
+            detail = L.aloha_group_last_error(h).decode() if h else ""
+            if h:
+                L.aloha_group_destroy(h)
+            raise AlohaError(rc, "group_create_local", detail)
+        return cls(h, L, engines)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.aloha_group_destroy(self.h)
+            self.h = None
+
+    def _ck(self, rc, what):
+        if rc:
+            raise AlohaError(rc, what, self.L.aloha_group_last_error(self.h).decode())
+
+    @property
+    def size(self) -> int:
+        return self.L.aloha_group_size(self.h)
+
+    @property
+    def rank(self) -> int:
+        return self.L.aloha_group_rank(self.h)
+
+    def all_gather_rows(self, spm_row: int, rows_per_rank: int, count: int = 1, stride_rows: int = 0, chunked=False):
+        self._ck(self.L.aloha_group_all_gather_rows(self.h, spm_row, rows_per_rank, count, stride_rows,
+                                                    GROUP_CHUNKED if chunked else 0), "group_all_gather_rows")
+
+    def broadcast_rows(self, spm_row: int, nrows: int, root: int):
+        self._ck(self.L.aloha_group_broadcast_rows(self.h, spm_row, nrows, root), "group_broadcast_rows")
+
+    def wait(self, source: int = GROUP_ALL):
+        self._ck(self.L.aloha_group_wait(self.h, source), "group_wait")
 
 
 class HostDriver:

@@ -8,8 +8,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, os.environ.get("ALOHA_LIB_NAME", "libaloha_b200.so"))
-SOURCES = ["ntt_kernels.cu", "ew_kernels.cu", "engine.cpp", "host.cpp"]
-HEADERS = ["kernels.cuh", "modarith.cuh", "engine.hpp", "isa.hpp", "../../include/aloha_b200.h"]
+SOURCES = ["ntt_kernels.cu", "ew_kernels.cu", "engine.cpp", "host.cpp", "group.cpp"]
+HEADERS = ["kernels.cuh", "modarith.cuh", "engine.hpp", "isa.hpp", "aut_plan.hpp", "../../include/aloha_b200.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"] + os.environ.get("ALOHA_NVCC_DEFS", "").split()

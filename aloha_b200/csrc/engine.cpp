@@ -1374,6 +1374,13 @@ int aloha_sync(aloha_t *E) {
     return ALOHA_OK;
 }
 
+int aloha_flush(aloha_t *E) {
+    if (!E) return ALOHA_E_ARG;
+    DeviceGuard dg_(E->device);
+    FLUSH();
+    return ALOHA_OK;
+}
+
 int aloha_spm_device_ptr(aloha_t *E, uint32_t row, void **p) {
     if (!E || !p) return ALOHA_E_ARG;
     DeviceGuard dg_(E->device);

@@ -1,0 +1,449 @@
+"""Generator for limb-sharded key-switch / relinearise / rescale instruction streams with dnum digits of
+alpha = ceil(L / dnum) limbs and K special primes (hybrid key switching), SURVEY 8(f)1.
+
+The reference ships ONE such kernel, sim/vp/isram_file_generator/keyswitch.mem (122 instructions; SURVEY
+App. B.4): L = 2 ciphertext primes, K = 1 special prime, one limb per digit (dnum = L).  Everything below is
+that kernel's instruction pattern with the two loops it has unrolled by hand made general:
+
+  * digits of alpha limbs.  A digit is the integer X_b < Q_b = prod_{j in G_b} q_j whose residues are the
+    coefficient-form limbs c_j.  Its image under another modulus m is the fast basis extension
+        ext_m(X_b) = sum_{j in G_b} [c_j * (Q_b/q_j)^-1 mod q_j] * (Q_b/q_j mod m)   (mod m),
+    i.e. per source limb one VFQMUL.vs (done once, by the limb's owner: d_j), then per target modulus a
+    VCPY / VFQMOD of d_j into the target modulus (the reference's own base-extension step, insts 8, 12, 28,
+    32), a VFQMUL.vs and a VFQADD.  With alpha = 1 both scalars are 1 and the multiplies are not emitted --
+    what remains is the reference's sequence word for word.
+  * K special primes.  The mod-down by P = prod p_k is the same extension from {p_k} to each q_i, with the
+    reference's rounding (add floor(P/2) before, subtract it after: insts 79-82, 85-88).  With K = 1 the
+    scalars are 1 and the sequence is the reference's.
+
+Phases (every phase is a set of independent per-limb streams; the machine that owns a limb runs its streams):
+  1  limb j < L:      c_j = VAUT(INTT(sw_j))   [no VAUT for relinearise],  d_j = c_j * qhatinv_j -> D[j]
+                      rotate only: a'_j = NTT(VAUT(INTT(a_j))) -> A'[j]
+     -- all-gather of D --
+  2  modulus t:       e_b = NTT_t(ext_t(digit b))  (own group: NTT_t(c_t)),  acc_t,c = sum_b e_b * KSK[t][b][c]
+                      special t = L + k: T[k][c] = (INTT(acc_t,c) + floor(P/2)) * phatinv_k
+     -- broadcast of T from the owners of the special primes --
+  3  limb i < L:      r_c = (acc_i,c - NTT_i(ext_i(T[.][c]) - floor(P/2))) * P^-1 ;  out_c = addend_c + r_c
+                      (rotate: addend_0 = a'_i, none for c = 1;  relinearise: addend_c = ct_c,i)
+Rescale (drop the last prime) is phase 2's special-prime tail and phase 3 on their own.
+
+Memory: only the three pointer CSRs (+ ksk_ptr) address memory and a VLE / VSE immediate reaches 65536 rows,
+so the SPM is laid out in regions of at most 65536 rows and each phase picks three of them.
+"""
+from __future__ import annotations
+
+from math import prod
+
+import numpy as np
+
+from . import asm
+
+
+def _ceil_div(a: int, b: int) -> int:
+    return -(-a // b)
+
+
+class Params:
+    """Scheme constants of one key-switch shape."""
+
+    def __init__(self, n: int, q: list[int], p: list[int], dnum: int | None = None):
+        self.n, self.rp = n, n // 128
+        self.q, self.p = list(q), list(p)
+        self.L, self.K = len(self.q), len(self.p)
+        dnum = self.L if dnum is None else dnum
+        assert 1 <= dnum <= self.L and self.K >= 1
+        self.alpha = _ceil_div(self.L, dnum)
+        self.groups = [list(range(b, min(b + self.alpha, self.L))) for b in range(0, self.L, self.alpha)]
+        self.dnum = len(self.groups)
+        self.moduli = self.q + self.p
+        self.group_of = {j: b for b, g in enumerate(self.groups) for j in g}
+        self.P = prod(self.p)
+        self.half = self.P // 2
+        self.qhat_inv, self.qhat_mod = {}, {}
+        for g in self.groups:
+            Qb = prod(self.q[j] for j in g)
+            for j in g:
+                qhat = Qb // self.q[j]
+                self.qhat_inv[j] = pow(qhat, -1, self.q[j])
+                for t, m in enumerate(self.moduli):
+                    if t not in g:
+                        self.qhat_mod[j, t] = qhat % m
+        self.phat_inv = [pow(self.P // pk, -1, pk) for pk in self.p]
+        self.phat_mod = {(k, i): (self.P // pk) % qi for k, pk in enumerate(self.p) for i, qi in enumerate(self.q)}
+        self.pinv = [pow(self.P, -1, qi) for qi in self.q]
+
+    def transform_count(self, kind: str = "rotate") -> int:
+        """limb-(I)NTTs of one key-switch"""
+        L, K = self.L, self.K
+        phase1 = 3 * L if kind == "rotate" else L
+        return phase1 + self.dnum * (L + K) + 2 * K + 2 * L
+
+
+class Layout:
+    """SPM / KSK row map and limb ownership for one machine of `world`, `batch` key-switches side by side."""
+
+    def __init__(self, prm: Params, world: int = 1, rank: int = 0, batch: int = 1, kind: str = "rotate"):
+        assert kind in ("rotate", "relin")
+        self.prm, self.world, self.rank, self.batch, self.kind = prm, world, rank, batch, kind
+        L, K, rp = prm.L, prm.K, prm.rp
+        self.nm = L + K
+        self.per_rank = _ceil_div(self.nm, world)
+        self.slots = self.per_rank * world
+        self.in_polys = (3 if kind == "relin" else 2) * L
+        self.IN_size = self.in_polys * rp                       # a | b | (d2)
+        self.S_size = (self.slots + L) * rp                     # D[slots] | A'[L]
+        self.ACC_size = (2 * self.nm + 2 * K) * rp              # acc[t][c] | T[k][c]
+        self.OUT_size = (2 * L + (L if prm.alpha > 1 else 0)) * rp   # out_0 | out_1 | C[L] (unscaled digits)
+        for name in ("IN_size", "S_size", "ACC_size", "OUT_size"):
+            if getattr(self, name) > 65536:
+                raise ValueError(f"region {name[:-5]} exceeds the 16-bit row offset of VLE/VSE; reduce L or N")
+        self.IN = 0
+        self.S = self.IN + batch * self.IN_size
+        self.ACC = self.S + batch * self.S_size
+        self.OUT = self.ACC + batch * self.ACC_size
+        self.spm_rows = self.OUT + batch * self.OUT_size
+        self.T_off = 2 * self.nm * rp                            # T inside the ACC region
+        self.ksk_slice_rows = 2 * prm.dnum * rp                  # KSK[t] = [b][c] polynomials under modulus t
+        self.ksk_rows = self.per_rank * self.ksk_slice_rows
+
+    def owner(self, limb: int) -> int:
+        return limb // self.per_rank
+
+    def owned(self, rank: int | None = None) -> list[int]:
+        r = self.rank if rank is None else rank
+        return [t for t in range(self.nm) if self.owner(t) == r]
+
+    def modulus(self, t: int) -> int:
+        return self.prm.moduli[t]
+
+    def ksk_ptr(self, t: int) -> int:
+        return (t - self.owner(t) * self.per_rank) * self.ksk_slice_rows
+
+    def region(self, name: str, b: int) -> int:
+        return getattr(self, name) + b * getattr(self, name + "_size")
+
+
+def _extend(p: asm.Program, src_mod: int, dst_mod: int, vd: int, vs: int):
+    """keyswitch.mem: VFQMOD when the source modulus is larger than the target (inst 28), VCPY when the
+    target is larger (insts 8, 12, 32)"""
+    (p.vfqmod if src_mod > dst_mod else p.vcpy)(vd, vs)
+
+
+def phase1_stream(lay: Layout, j: int) -> asm.Program:
+    """src0 = IN, src1 = S, rslt = OUT.  Registers as keyswitch.mem insts 3-5, 17-20."""
+    prm, rp, L = lay.prm, lay.prm.rp, lay.prm.L
+    p = asm.Program().vsetvl(prm.n).vsetq(prm.q[j])
+    if lay.kind == "rotate":
+        p.vle(4, asm.BASE_SRC0, (L + j) * rp).vintt(2, 4).vaut(4, 2)
+        c = 4
+    else:
+        p.vle(4, asm.BASE_SRC0, (2 * L + j) * rp).vintt(2, 4)
+        c = 2
+    if prm.alpha == 1:
+        p.vse(c, asm.BASE_SRC1, j * rp)
+    else:
+        p.vse(c, asm.BASE_RSLT, (2 * L + j) * rp)
+        p.vfqmul(8, c, imm=prm.qhat_inv[j]).vse(8, asm.BASE_SRC1, j * rp)
+    if lay.kind == "rotate":
+        p.vle(3, asm.BASE_SRC0, j * rp).vintt(6, 3).vaut(3, 6).vntt(2, 3).vse(2, asm.BASE_SRC1, (lay.slots + j) * rp)
+    return p.brk()
+
+
+def phase2_stream(lay: Layout, t: int, groups: list[int] | None = None, first: bool = True, last: bool = True) -> asm.Program:
+    """src0 = S (gathered digits), src1 = OUT (unscaled own digits), rslt = ACC, base 15 = KSK[t].
+    `groups` restricts the stream to some digits (a machine can start on the digits it already holds while the
+    others are in flight); `first` / `last` say whether the accumulators start here / are finished here."""
+    prm, rp, L, K = lay.prm, lay.prm.rp, lay.prm.L, lay.prm.K
+    mt = prm.moduli[t]
+    groups = list(range(prm.dnum)) if groups is None else groups
+    p = asm.Program().vsetvl(prm.n).vsetq(mt)
+    acc_row = lambda c: (2 * t + c) * rp
+    if not first:
+        p.vle(4, asm.BASE_RSLT, acc_row(0)).vle(6, asm.BASE_RSLT, acc_row(1))
+    started = not first
+    for b in groups:
+        g = prm.groups[b]
+        if t in g:
+            if prm.alpha == 1:
+                p.vle(0, asm.BASE_SRC0, t * rp)
+            else:
+                p.vle(0, asm.BASE_SRC1, (2 * L + t) * rp)
+            src = 0
+        elif prm.alpha == 1:
+            j = g[0]
+            p.vle(0, asm.BASE_SRC0, j * rp)
+            _extend(p, prm.q[j], mt, 8, 0)
+            src = 8
+        else:
+            for n_, j in enumerate(g):
+                p.vle(0, asm.BASE_SRC0, j * rp)
+                _extend(p, prm.q[j], mt, 8, 0)
+                if n_ == 0:
+                    p.vfqmul(13, 8, imm=prm.qhat_mod[j, t])
+                else:
+                    p.vfqmul(10, 8, imm=prm.qhat_mod[j, t]).vfqadd(13, 13, 10)
+            src = 13
+        p.vntt(2, src)
+        for c in (0, 1):
+            k, prod_, acc = 1 + 2 * c, 5 + 2 * c, 4 + 2 * c          # odd key reg, odd product, even accumulator
+            p.vle(k, asm.BASE_KSK, (2 * b + c) * rp)
+            if not started:
+                p.vfqmul(acc, 2, k)
+            else:
+                p.vfqmul(prod_, 2, k).vfqadd(acc, acc, prod_)
+        started = True
+    if not last or t < L:
+        p.vse(4, asm.BASE_RSLT, acc_row(0)).vse(6, asm.BASE_RSLT, acc_row(1))
+    else:
+        k = t - L
+        half = prm.half % mt                                          # keyswitch.mem insts 79-82
+        for c, (acc, tmp, out) in enumerate(((4, 8, 10), (6, 9, 11))):
+            p.vintt(tmp, acc).vfqadd(out, tmp, imm=half)
+            if K > 1:
+                p.vfqmul(12 + c, out, imm=prm.phat_inv[k])
+                out = 12 + c
+            p.vse(out, asm.BASE_RSLT, lay.T_off + (2 * k + c) * rp)
+    return p.brk()
+
+
+def phase3_stream(lay: Layout, i: int) -> asm.Program:
+    """src0 = ACC (+T), src1 = S (rotate: A') or IN (relinearise: the addends), rslt = OUT.  keyswitch.mem insts 85-120."""
+    prm, rp, L, K = lay.prm, lay.prm.rp, lay.prm.L, lay.prm.K
+    qi = prm.q[i]
+    p = asm.Program().vsetvl(prm.n).vsetq(qi)
+    for c in (0, 1):
+        if K == 1:
+            p.vle(0, asm.BASE_SRC0, lay.T_off + c * rp).vfqsub(2, 0, imm=prm.half % qi)
+        else:
+            for k in range(K):
+                p.vle(0, asm.BASE_SRC0, lay.T_off + (2 * k + c) * rp)
+                _extend(p, prm.p[k], qi, 8, 0)
+                if k == 0:
+                    p.vfqmul(13, 8, imm=prm.phat_mod[k, i])
+                else:
+                    p.vfqmul(10, 8, imm=prm.phat_mod[k, i]).vfqadd(13, 13, 10)
+            p.vfqsub(2, 13, imm=prm.half % qi)
+        p.vntt(4, 2)
+        p.vle(1, asm.BASE_SRC0, (2 * i + c) * rp).vfqsub(6, 1, 4).vfqmul(8, 6, imm=prm.pinv[i])
+        if lay.kind == "rotate":
+            if c == 0:
+                p.vle(3, asm.BASE_SRC1, (lay.slots + i) * rp).vfqadd(10, 3, 8).vse(10, asm.BASE_RSLT, i * rp)
+            else:
+                p.vse(8, asm.BASE_RSLT, (L + i) * rp)
+        else:
+            p.vle(3, asm.BASE_SRC1, (c * L + i) * rp).vfqadd(10, 3, 8).vse(10, asm.BASE_RSLT, (c * L + i) * rp)
+    return p.brk()
+
+
+# ---------------------------------------------------------------------------------------------- exchange
+class LocalComm:
+    """world = 1: no exchange."""
+    world, rank = 1, 0
+
+    def all_gather(self, machine, row, rows_per_rank, count, stride, chunked=False):
+        pass
+
+    def broadcast(self, machine, row, nrows, root, count, stride):
+        pass
+
+    def wait(self, machine, source=-1):
+        pass
+
+
+class GroupComm:
+    """The product path: NCCL inside the C library (aloha_group_*), transfers beside the kernels."""
+
+    def __init__(self, group):
+        self.group, self.world, self.rank = group, group.size, group.rank
+
+    def all_gather(self, machine, row, rows_per_rank, count, stride, chunked=False):
+        self.group.all_gather_rows(row, rows_per_rank, count, stride, chunked)
+
+    def broadcast(self, machine, row, nrows, root, count, stride):
+        for c in range(count):
+            self.group.broadcast_rows(row + c * stride, nrows, root)
+
+    def wait(self, machine, source=-1):
+        self.group.wait(source)
+
+
+class TorchComm:
+    """torch.distributed exchange staged through host arrays: for machines without device memory (the CPU
+    oracle under gloo in the tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def all_gather(self, machine, row, rows_per_rank, count, stride, chunked=False):
+        import torch
+        for c in range(count):
+            base = row + c * stride
+            mine = torch.from_numpy(machine.dma_mem_d2h(base + self.rank * rows_per_rank, rows_per_rank * 128).view(np.int64))
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            self.dist.all_gather(parts, mine, group=self.group)
+            machine.dma_mem_h2d(base, np.concatenate([x.numpy() for x in parts]).view(np.uint64))
+
+    def broadcast(self, machine, row, nrows, root, count, stride):
+        import torch
+        for c in range(count):
+            t = torch.from_numpy(machine.dma_mem_d2h(row + c * stride, nrows * 128).view(np.int64).copy())
+            self.dist.broadcast(t, src=root, group=self.group)
+            machine.dma_mem_h2d(row + c * stride, t.numpy().view(np.uint64))
+
+    def wait(self, machine, source=-1):
+        pass
+
+
+class KeySwitch:
+    """Runs the three phases on one machine (anything with the Engine method set) of a group.
+    overlap: phase 2 is cut by the rank that owns each digit's limbs; the all-gather moves one source rank at
+    a time and the machine starts on the digits that have arrived (its own first)."""
+
+    def __init__(self, machine, lay: Layout, comm=None, pc_base: int = 0, overlap: bool = False):
+        self.machine, self.lay, self.comm = machine, lay, comm or LocalComm()
+        assert self.comm.world == lay.world and self.comm.rank == lay.rank
+        prm = lay.prm
+        self.overlap = overlap and lay.world > 1
+        # digits whose source limbs all live on rank r can be consumed as soon as r's block has arrived;
+        # a digit that straddles two ranks waits for the later one
+        self.digit_rank = [max(lay.owner(j) for j in g) for g in prm.groups]
+        self.pc1, self.pc2, self.pc3 = {}, {}, {}
+        pc = pc_base
+
+        def put(table, key, prog):
+            nonlocal pc
+            words = prog.words()
+            machine.load_isram(words, pc)
+            table[key] = pc
+            pc += len(words)
+        for t in lay.owned():
+            if t < prm.L:
+                put(self.pc1, t, phase1_stream(lay, t))
+                put(self.pc3, t, phase3_stream(lay, t))
+            if not self.overlap:
+                put(self.pc2, (t, None), phase2_stream(lay, t))
+            else:
+                order = self.chunk_order()
+                for n_, r in enumerate(order):
+                    gs = [b for b in range(prm.dnum) if self.digit_rank[b] == r]
+                    put(self.pc2, (t, r), phase2_stream(lay, t, gs, first=n_ == 0, last=n_ == len(order) - 1))
+        self.pc_end = pc
+
+    def chunk_order(self) -> list[int]:
+        """source ranks in the order phase 2 consumes them: own digits first, then the order of arrival"""
+        have = sorted({r for r in self.digit_rank})
+        return [r for r in have if r == self.lay.rank] + [r for r in have if r != self.lay.rank]
+
+    def load_ksk(self, t: int, data: np.ndarray):
+        """data: KSK[t] = 2 dnum polynomials ([b][c] order) under modulus t; only the owner stores it."""
+        lay = self.lay
+        assert lay.owner(t) == lay.rank and data.size == 2 * lay.prm.dnum * lay.prm.n
+        self.machine.dma_ksk_h2d(lay.ksk_ptr(t), data.reshape(-1))
+
+    def load_input(self, i: int, polys, b: int = 0):
+        """polys: (a_i, b_i) for rotate, (d0_i, d1_i, d2_i) for relinearise -- limb i of batch element b"""
+        lay, rp, L = self.lay, self.lay.prm.rp, self.lay.prm.L
+        for c, x in enumerate(polys):
+            self.machine.dma_mem_h2d(lay.region("IN", b) + (c * L + i) * rp, x)
+
+    def run(self, galois_k: int = 1, only: list[int] | None = None):
+        """only: restrict phases 2 and 3 to these output limbs (+ the special primes) -- for checks that want
+        a few output limbs without paying for all of them."""
+        lay, m, prm = self.lay, self.machine, self.lay.prm
+        B, rp = lay.batch, prm.rp
+        mine = lay.owned()
+        want = lambda t: only is None or t >= prm.L or t in only
+        reg = lay.region
+        m.run_vp_multi([(self.pc1[j], reg("IN", b), reg("S", b), reg("OUT", b), 0, galois_k)
+                        for b in range(B) for j in mine if j < prm.L])
+        self.comm.all_gather(m, lay.S, lay.per_rank * rp, B, lay.S_size, chunked=self.overlap)
+        if not self.overlap:
+            self.comm.wait(m, -1)
+            m.run_vp_multi([(self.pc2[t, None], reg("S", b), reg("OUT", b), reg("ACC", b), lay.ksk_ptr(t), 0)
+                            for b in range(B) for t in mine if want(t)])
+        else:
+            for r in self.chunk_order():
+                if r != lay.rank:
+                    self.comm.wait(m, r)
+                m.run_vp_multi([(self.pc2[t, r], reg("S", b), reg("OUT", b), reg("ACC", b), lay.ksk_ptr(t), 0)
+                                for b in range(B) for t in mine if want(t)])
+        for r in range(lay.world):
+            ks = [t - prm.L for t in lay.owned(r) if t >= prm.L]
+            if ks:
+                self.comm.broadcast(m, lay.ACC + lay.T_off + 2 * ks[0] * rp, 2 * len(ks) * rp, r, B, lay.ACC_size)
+        self.comm.wait(m, -2)
+        src1 = "S" if lay.kind == "rotate" else "IN"
+        m.run_vp_multi([(self.pc3[i], reg("ACC", b), reg(src1, b), reg("OUT", b), 0, 0)
+                        for b in range(B) for i in mine if i < prm.L and want(i)])
+
+    def read_output(self, i: int, b: int = 0):
+        lay, rp, L = self.lay, self.lay.prm.rp, self.lay.prm.L
+        out = lay.region("OUT", b)
+        return (self.machine.dma_mem_d2h(out + i * rp, lay.prm.n), self.machine.dma_mem_d2h(out + (L + i) * rp, lay.prm.n))
+
+
+# ------------------------------------------------------------------------------------------------ rescale
+class Rescale:
+    """Drop the last ciphertext prime: per remaining limb i and component c
+        out_c,i = (ct_c,i - NTT_i(ext_i(INTT(ct_c,last)) + round)) * q_last^-1  (mod q_i),
+    the same instruction pattern as the key-switch's mod-down (keyswitch.mem insts 79-120) with P = q_last.
+    Regions: IN = ct (2 L polys) , T (2 polys), OUT (2 (L-1) polys)."""
+
+    def __init__(self, machine, n: int, q: list[int], world: int = 1, rank: int = 0, comm=None, pc_base: int = 0):
+        self.machine, self.n, self.q, self.rp = machine, n, list(q), n // 128
+        self.comm = comm or LocalComm()
+        self.world, self.rank = world, rank
+        L, rp = len(self.q), self.rp
+        self.L = L
+        self.per_rank = _ceil_div(L, world)
+        self.IN, self.T, self.OUT = 0, 2 * L * rp, (2 * L + 2) * rp
+        self.spm_rows = self.OUT + 2 * (L - 1) * rp
+        if 2 * L * rp > 65536:
+            raise ValueError("region exceeds the 16-bit row offset of VLE/VSE")
+        ql = self.q[-1]
+        half = ql // 2
+        self.pc_t, self.pc_out = None, {}
+        pc = pc_base
+        if self.owner(L - 1) == rank:
+            p = asm.Program().vsetvl(n).vsetq(ql)
+            for c in (0, 1):
+                p.vle(4, asm.BASE_SRC0, (c * L + L - 1) * rp).vintt(8, 4).vfqadd(10, 8, imm=half).vse(10, asm.BASE_RSLT, c * rp)
+            words = p.brk().words()
+            machine.load_isram(words, pc)
+            self.pc_t = pc
+            pc += len(words)
+        for i in range(L - 1):
+            if self.owner(i) != rank:
+                continue
+            qi = self.q[i]
+            p = asm.Program().vsetvl(n).vsetq(qi)
+            for c in (0, 1):
+                p.vle(0, asm.BASE_SRC1, c * rp).vfqsub(2, 0, imm=half % qi).vntt(4, 2)
+                p.vle(1, asm.BASE_SRC0, (c * L + i) * rp).vfqsub(6, 1, 4).vfqmul(8, 6, imm=pow(ql, -1, qi))
+                p.vse(8, asm.BASE_RSLT, (c * (L - 1) + i) * rp)
+            words = p.brk().words()
+            machine.load_isram(words, pc)
+            self.pc_out[i] = pc
+            pc += len(words)
+        self.pc_end = pc
+
+    def owner(self, i: int) -> int:
+        return i // self.per_rank
+
+    def load_input(self, i: int, c0: np.ndarray, c1: np.ndarray):
+        self.machine.dma_mem_h2d(self.IN + i * self.rp, c0)
+        self.machine.dma_mem_h2d(self.IN + (self.L + i) * self.rp, c1)
+
+    def run(self):
+        m = self.machine
+        if self.pc_t is not None:
+            m.run_vp(self.pc_t, self.IN, 0, self.T, 0, 0)
+        self.comm.broadcast(m, self.T, 2 * self.rp, self.owner(self.L - 1), 1, 0)
+        self.comm.wait(m, -2)
+        m.run_vp_multi([(pc, self.IN, self.T, self.OUT, 0, 0) for pc in self.pc_out.values()])
+
+    def read_output(self, i: int):
+        return (self.machine.dma_mem_d2h(self.OUT + i * self.rp, self.n),
+                self.machine.dma_mem_d2h(self.OUT + (self.L - 1 + i) * self.rp, self.n))

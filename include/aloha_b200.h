@@ -21,6 +21,11 @@
  *                                  architecturally identical to a loop over aloha_run_vp, handed to
  *                                  the batcher in one piece so independent limbs share launches
  *   aloha_run_vp_multi             ditto, one start pc per call
+ *   aloha_flush                    (ALOHA_F_DEFER) launch what has been queued, without waiting
+ *   aloha_group_*                  no counterpart on the single-chip reference: the DMA block's shape
+ *                                  (SPM rows, asynchronous, start/done ordering) extended to scratchpad-to-
+ *                                  scratchpad transfers between the engines of a limb-sharded machine; NCCL
+ *                                  over NVLink underneath (SURVEY 8(b) `n_gpus`, 8(e))
  *   aloha_host_*                   the testbench's host driver        sim/top/top_noaxilite_tb.sv:249-298 (parse_op),
  *                                                                     :419-532 (run_* tasks), :536-565 (dump_poly), :596-638 (run)
  *
@@ -44,6 +49,7 @@ extern "C" {
 
 typedef struct aloha aloha_t;
 typedef struct aloha_host aloha_host_t;
+typedef struct aloha_group aloha_group_t;
 
 enum {
     ALOHA_OK = 0,
@@ -142,6 +148,8 @@ int aloha_run_vp_batch(aloha_t *, uint32_t pc, uint32_t count, const aloha_vp_ar
  * per-modulus sections of a key-switch stream whose VSETQ immediates differ). */
 int aloha_run_vp_multi(aloha_t *, uint32_t count, const uint32_t *pcs, const aloha_vp_args *args);
 int aloha_sync(aloha_t *);
+/* ALOHA_F_DEFER: plan and launch everything queued so far; does not wait for the device. */
+int aloha_flush(aloha_t *);
 
 /* Zero-copy access for callers that already live on the device (and for the multi-GPU host layer,
  * which hands these to NCCL): device address of an SPM / KSK row.  Writes through these pointers
@@ -158,6 +166,40 @@ int aloha_get_csr(const aloha_t *, uint64_t *vl, uint64_t *q, uint64_t *iq);
  * (vxu cfg, scalar cfg, b0r, b0w, b1r, b1w, alu, scalar alu, iconn, scalar iconn, ntt, muxo, muxi,
  * vmu cfg, vmu scalar cfg, ls op, ls scalar). */
 int aloha_decode(const uint8_t word[12], uint64_t csr_step, uint64_t out[17]);
+
+/* ---- limb-sharded machine: several engines (one per GPU) exchanging SPM rows over NVLink -----------
+ * RNS limbs are independent units: every engine holds its limbs' slice of each polynomial, its twiddles and
+ * its KSK slices, and runs the same instruction streams on them.  The only cross-limb step of the path is
+ * the base extension of the key-switch stream (keyswitch.mem insts 8, 12, 28, 32 generalised): before it the
+ * coefficient-form digits are all-gathered, and before the mod-down the special-prime accumulators are
+ * broadcast.  Two ways to form a group:
+ *   one process per GPU   rank 0 calls aloha_group_unique_id and ships the 128 bytes to the other ranks by
+ *                         whatever channel the host program has; every rank calls aloha_group_create;
+ *   one process, n GPUs   aloha_group_create_local over engines created on n different devices (the
+ *                         testbench-shaped caller of INTEGRATION.md); member i has rank i and every group call
+ *                         acts on all members at once.
+ * Transfers run on a communication stream per device, ordered after all engine work issued before the call
+ * (like the DMA block next to the VP); aloha_group_wait orders later engine work after a transfer.  Rows of a
+ * transfer in flight must not be written by engine work issued before the matching wait. */
+enum { ALOHA_GROUP_ID_BYTES = 128 };
+enum { ALOHA_GROUP_CHUNKED = 1u };                     /* all-gather as one transfer per source rank */
+enum { ALOHA_GROUP_ALL = -1, ALOHA_GROUP_BCAST = -2 };  /* aloha_group_wait sources */
+int aloha_group_unique_id(uint8_t id[ALOHA_GROUP_ID_BYTES]);
+int aloha_group_create(aloha_t *engine, const uint8_t id[ALOHA_GROUP_ID_BYTES], int rank, int nranks,
+                       aloha_group_t **out);
+int aloha_group_create_local(aloha_t *const *engines, int n, aloha_group_t **out);
+void aloha_group_destroy(aloha_group_t *);
+int aloha_group_size(const aloha_group_t *);
+int aloha_group_rank(const aloha_group_t *);
+const char *aloha_group_last_error(const aloha_group_t *);
+/* `count` all-gathers issued as one transfer, the c-th over the rows starting at spm_row + c*stride_rows:
+ * rank r contributes rows [start + r*rows_per_rank, +rows_per_rank) of its SPM; all members end up with all
+ * blocks.  (count > 1: the digit regions of a batch of key-switches.) */
+int aloha_group_all_gather_rows(aloha_group_t *, uint32_t spm_row, uint32_t rows_per_rank, uint32_t count,
+                                uint32_t stride_rows, uint32_t flags);
+int aloha_group_broadcast_rows(aloha_group_t *, uint32_t spm_row, uint32_t nrows, int root);
+/* source >= 0: that rank's block of the latest all-gather; ALOHA_GROUP_ALL; ALOHA_GROUP_BCAST */
+int aloha_group_wait(aloha_group_t *, int source);
 
 /* ---- host driver: the testbench's op-list replay ------------------------------------------- */
 /* PROGRAM text: one op per line, "a0,a1,a2" hex u32 (top_noaxilite_tb.sv:249-298).  dram_bytes is
