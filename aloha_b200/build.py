@@ -8,8 +8,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, os.environ.get("ALOHA_LIB_NAME", "libaloha_b200.so"))
+REPLAY = os.path.join(HERE, "aloha_group_replay")
 SOURCES = ["ntt_kernels.cu", "ew_kernels.cu", "engine.cpp", "host.cpp", "group.cpp"]
-HEADERS = ["kernels.cuh", "modarith.cuh", "engine.hpp", "isa.hpp", "aut_plan.hpp", "../../include/aloha_b200.h"]
+HEADERS = ["group_replay_main.cpp", "kernels.cuh", "modarith.cuh", "engine.hpp", "isa.hpp", "aut_plan.hpp", "../../include/aloha_b200.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"] + os.environ.get("ALOHA_NVCC_DEFS", "").split()
@@ -42,6 +43,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose or "warning" in out:
             sys.stderr.write(out)
     subprocess.check_call([NVCC, "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    # the C host program for limb-sharded cases: sees nothing but include/aloha_b200.h and the library
+    subprocess.check_call([os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", os.path.join(CSRC, "group_replay_main.cpp"),
+                           "-o", REPLAY, "-L" + HERE, "-l:" + os.path.basename(LIB), "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 

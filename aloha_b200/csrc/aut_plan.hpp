@@ -92,6 +92,68 @@ ALOHA_HD void aut_store_slot(const AutTile &t, uint32_t s, uint32_t *jl, uint32_
     *jl = s >> t.log_fb; *fl = s & ((1u << t.log_fb) - 1);
 }
 
+// ---- how a thread walks its slots ----------------------------------------------------------------------
+// A thread's slots are kAutThreads apart (slot = it * 256 + tid).  From one slot to the next either the fast
+// coordinate advances by 256 (block side > 256: WIDE; it wraps into the slow one every side / 256 steps, for
+// the whole CTA at once) or the slow coordinate advances by 256 / side.  Source index, destination index and
+// shared-memory word therefore advance by per-CTA constants; aut_src / aut_dst are evaluated once per thread.
+template <bool WIDE>
+struct AutWalk {                 // coordinates (fast, slow) of a block whose fast side is 2^log_side
+    uint32_t fast, slow, side, step_slow;
+    ALOHA_HD AutWalk(uint32_t tid, uint32_t log_side)
+        : fast(tid & ((1u << log_side) - 1)), slow(tid >> log_side), side(1u << log_side), step_slow(kAutThreads >> log_side) {}
+    // advance by 256 slots; true when the fast coordinate wrapped (WIDE only; uniform over the CTA)
+    ALOHA_HD bool next() {
+        if (!WIDE) { slow += step_slow; return false; }
+        fast += kAutThreads;
+        if (fast >= side) { fast -= side; ++slow; return true; }
+        return false;
+    }
+};
+
+// load phase: fast = jl (lanes along the source), slow = fl
+template <bool WIDE>
+struct AutLoadWalk {
+    AutWalk<WIDE> w;
+    uint32_t i, sm;              // source index, shared-memory word
+    uint32_t di, di_wrap, dsm, dsm_wrap, mask, jcount, fcount;
+    ALOHA_HD AutLoadWalk(const AutPlan &p, const AutTile &t, uint32_t tid)
+        : w(tid, t.log_jb), i(aut_src(p, t, w.fast, w.slow)), sm(w.slow * t.stride + w.fast),
+          di(WIDE ? kAutThreads : w.step_slow * p.kinv), di_wrap(p.kinv - w.side),
+          dsm(WIDE ? kAutThreads : w.step_slow * t.stride), dsm_wrap(t.stride - w.side), mask(p.mask),
+          jcount(t.jcount), fcount(t.fcount) {}
+    ALOHA_HD bool idle() const { return !WIDE && w.fast >= jcount; }     // narrow block: fast never changes
+    ALOHA_HD bool valid() const { return (!WIDE || w.fast < jcount) && w.slow < fcount; }
+    ALOHA_HD void next() {
+        i += di; sm += dsm;
+        if (w.next()) { i += di_wrap; sm += dsm_wrap; }
+        i &= mask;
+    }
+};
+
+// store phase: fast = fl (lanes along the destination), slow = jl
+template <bool WIDE>
+struct AutStoreWalk {
+    AutWalk<WIDE> w;
+    uint32_t i, d, sm;           // source index (for the sign), destination index, shared-memory word
+    uint32_t di, di_wrap, dd, dd_wrap, dsm, dsm_wrap, mask, jcount, fcount;
+    ALOHA_HD AutStoreWalk(const AutPlan &p, const AutTile &t, uint32_t tid)
+        : w(tid, t.log_fb), i(aut_src(p, t, w.slow, w.fast)), d(aut_dst(p, t, w.slow, w.fast)), sm(w.fast * t.stride + w.slow),
+          di(WIDE ? kAutThreads * p.kinv : w.step_slow), di_wrap(1u - w.side * p.kinv),
+          dd(WIDE ? kAutThreads : w.step_slow * p.kmod), dd_wrap(p.kmod - w.side),
+          dsm(WIDE ? kAutThreads * t.stride : w.step_slow), dsm_wrap(1u - w.side * t.stride), mask(p.mask),
+          jcount(t.jcount), fcount(t.fcount) {}
+    ALOHA_HD bool idle() const { return !WIDE && w.fast >= fcount; }
+    ALOHA_HD bool valid() const { return w.slow < jcount && (!WIDE || w.fast < fcount); }
+    ALOHA_HD void next() {
+        i += di; d += dd; sm += dsm;
+        if (w.next()) { i += di_wrap; d += dd_wrap; sm += dsm_wrap; }
+        i &= mask; d &= mask;
+    }
+};
+// (i * k) mod 2n >= n  <=>  bit log2(n) of i * k: 32-bit arithmetic is enough (the bit sits below bit 32)
+ALOHA_HD bool aut_negated(uint32_t i, uint32_t k2, uint32_t n) { return ((i * k2) & n) != 0; }
+
 namespace autdetail {
 
 inline uint32_t clog2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) ++l; return l; }

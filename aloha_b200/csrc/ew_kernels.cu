@@ -9,6 +9,7 @@
 // All of them are HBM-bound streams: 16-byte vector accesses, one job table per launch
 // (blockIdx.y = job), grids sized so every SM holds several CTAs.
 #include <atomic>
+#include <type_traits>
 
 #include "kernels.cuh"
 #include "modarith.cuh"
@@ -145,50 +146,55 @@ __global__ void __launch_bounds__(kThreads) autmac_kernel(const AutMacJob *__res
 constexpr int kAutIters = kAutTile / kThreads;      // 8 slots per thread
 static_assert(kThreads == (int)kAutThreads, "aut_plan.hpp replays the kernels with this block size");
 
+// Index arithmetic is incremental (aut_plan.hpp AutLoadWalk / AutStoreWalk, the same code the CPU model in
+// tests/native replays): per-CTA constant steps, aut_src / aut_dst evaluated once per thread.
 template <bool MAC, class Job>
 __device__ __forceinline__ void aut_tile_body(const Job &job, u32 n, u64 *tile) {
     const AutPlan &P = job.plan;
     const AutTile T = aut_tile(P, blockIdx.x);
-    const u32 slots = 1u << (T.log_jb + T.log_fb);
     const u64 *__restrict__ src;
     if constexpr (MAC) src = job.x; else src = job.src;
-    // load: slot s = fl * JB + jl
-    u64 v[kAutIters];
+    u64 *__restrict__ dst = job.dst;
+    const u64 q = job.q;
+    const u32 k2 = (u32)job.k & (2 * n - 1);
+    // ---- load: cp.async (LDGSTS) straight into the tile, lanes along the source
+    auto load = [&](auto wide) {
+        AutLoadWalk<decltype(wide)::value> w(P, T, threadIdx.x);
+        if (w.idle()) return;
+        const u32 tile_addr = (u32)__cvta_generic_to_shared(tile);
 #pragma unroll
-    for (int it = 0; it < kAutIters; ++it) {
-        u32 jl, fl;
-        const u32 s = it * kThreads + threadIdx.x;
-        aut_load_slot(T, s, &jl, &fl);
-        if (s < slots && jl < T.jcount && fl < T.fcount) v[it] = __ldg(src + aut_src(P, T, jl, fl));
-    }
-#pragma unroll
-    for (int it = 0; it < kAutIters; ++it) {
-        u32 jl, fl;
-        const u32 s = it * kThreads + threadIdx.x;
-        aut_load_slot(T, s, &jl, &fl);
-        if (s < slots && jl < T.jcount && fl < T.fcount) tile[fl * T.stride + jl] = v[it];
-    }
-    __syncthreads();
-    // store: slot s = jl * FB + fl
-    const u64 q = job.q, k2 = job.k & (2ull * n - 1);
-#pragma unroll
-    for (int it = 0; it < kAutIters; ++it) {
-        u32 jl, fl;
-        const u32 s = it * kThreads + threadIdx.x;
-        aut_store_slot(T, s, &jl, &fl);
-        if (s < slots && jl < T.jcount && fl < T.fcount) {
-            const u32 i = aut_src(P, T, jl, fl), d = aut_dst(P, T, jl, fl);
-            const u64 x = tile[fl * T.stride + jl];
-            const bool neg = (((u64)i * k2) & (2ull * n - 1)) >= n;
-            const u64 y = neg ? q - x : x;
-            if constexpr (MAC) {
-                const u64 m = rtl_alu<ALU_MUL_VV>(y, job.p[d], 0, q, job.iq);
-                job.dst[d] = rtl_alu<ALU_ADD_VV>(job.c[d], m, 0, q, job.iq);
-            } else {
-                job.dst[d] = y;
-            }
+        for (int it = 0; it < kAutIters; ++it) {
+            if (w.valid())
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile_addr + w.sm * 8), "l"(src + w.i) : "memory");
+            w.next();
         }
-    }
+    };
+    if (T.log_jb > 8) load(std::true_type{}); else load(std::false_type{});
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    // ---- store: lanes along the destination
+    auto store = [&](auto wide) {
+        AutStoreWalk<decltype(wide)::value> w(P, T, threadIdx.x);
+        if (w.idle()) return;
+        [[maybe_unused]] const u64 *__restrict__ pp = nullptr, *__restrict__ cc = nullptr;
+        [[maybe_unused]] u64 iq = 0;
+        if constexpr (MAC) { pp = job.p; cc = job.c; iq = job.iq; }
+#pragma unroll
+        for (int it = 0; it < kAutIters; ++it) {
+            if (w.valid()) {
+                const u64 x = tile[w.sm];
+                const u64 y = aut_negated(w.i, k2, n) ? q - x : x;
+                if constexpr (MAC) {
+                    const u64 m = rtl_alu<ALU_MUL_VV>(y, pp[w.d], 0, q, iq);
+                    dst[w.d] = rtl_alu<ALU_ADD_VV>(cc[w.d], m, 0, q, iq);
+                } else {
+                    dst[w.d] = y;
+                }
+            }
+            w.next();
+        }
+    };
+    if (T.log_fb > 8) store(std::true_type{}); else store(std::false_type{});
 }
 
 __global__ void __launch_bounds__(kThreads) vaut_tiled_kernel(const AutJob *__restrict__ jobs, u32 n) {

@@ -301,8 +301,10 @@ class KeySwitch:
     overlap: phase 2 is cut by the rank that owns each digit's limbs; the all-gather moves one source rank at
     a time and the machine starts on the digits that have arrived (its own first)."""
 
-    def __init__(self, machine, lay: Layout, comm=None, pc_base: int = 0, overlap: bool = False):
-        self.machine, self.lay, self.comm = machine, lay, comm or LocalComm()
+    def __init__(self, machine, lay: Layout, comm=None, pc_base: int = 0, overlap: bool = False, lockstep: bool = False):
+        """lockstep: every rank consumes the chunks in the same order and waits for each of them, its own
+        included -- what a single host thread driving all machines of a local group needs (run_local_group)."""
+        self.machine, self.lay, self.comm, self.lockstep = machine, lay, comm or LocalComm(), lockstep
         assert self.comm.world == lay.world and self.comm.rank == lay.rank
         prm = lay.prm
         self.overlap = overlap and lay.world > 1
@@ -334,6 +336,8 @@ class KeySwitch:
     def chunk_order(self) -> list[int]:
         """source ranks in the order phase 2 consumes them: own digits first, then the order of arrival"""
         have = sorted({r for r in self.digit_rank})
+        if self.lockstep:
+            return have
         return [r for r in have if r == self.lay.rank] + [r for r in have if r != self.lay.rank]
 
     def load_ksk(self, t: int, data: np.ndarray):
@@ -348,40 +352,147 @@ class KeySwitch:
         for c, x in enumerate(polys):
             self.machine.dma_mem_h2d(lay.region("IN", b) + (c * L + i) * rp, x)
 
-    def run(self, galois_k: int = 1, only: list[int] | None = None):
-        """only: restrict phases 2 and 3 to these output limbs (+ the special primes) -- for checks that want
-        a few output limbs without paying for all of them."""
-        lay, m, prm = self.lay, self.machine, self.lay.prm
+    def program(self, galois_k: int = 1, only: list[int] | None = None) -> list[tuple]:
+        """The key-switch as a list of machine-level ops, in issue order:
+             ("run", [(pc, src0, src1, rslt, ksk_ptr, step), ...])        one aloha_run_vp_multi
+             ("all_gather", row, rows_per_rank, count, stride, chunked)   aloha_group_all_gather_rows
+             ("broadcast", row, nrows, root, count, stride)               aloha_group_broadcast_rows (x count)
+             ("wait", source)                                             aloha_group_wait
+        Every rank's list has the same collectives in the same order.
+        only: restrict phases 2 and 3 to these output limbs (+ the special primes) -- for checks that want a
+        few output limbs without paying for all of them."""
+        lay, prm = self.lay, self.lay.prm
         B, rp = lay.batch, prm.rp
         mine = lay.owned()
         want = lambda t: only is None or t >= prm.L or t in only
         reg = lay.region
-        m.run_vp_multi([(self.pc1[j], reg("IN", b), reg("S", b), reg("OUT", b), 0, galois_k)
-                        for b in range(B) for j in mine if j < prm.L])
-        self.comm.all_gather(m, lay.S, lay.per_rank * rp, B, lay.S_size, chunked=self.overlap)
+        ops = [("run", [(self.pc1[j], reg("IN", b), reg("S", b), reg("OUT", b), 0, galois_k)
+                        for b in range(B) for j in mine if j < prm.L])]
+        ops.append(("all_gather", lay.S, lay.per_rank * rp, B, lay.S_size, self.overlap))
         if not self.overlap:
-            self.comm.wait(m, -1)
-            m.run_vp_multi([(self.pc2[t, None], reg("S", b), reg("OUT", b), reg("ACC", b), lay.ksk_ptr(t), 0)
-                            for b in range(B) for t in mine if want(t)])
+            ops.append(("wait", -1))
+            ops.append(("run", [(self.pc2[t, None], reg("S", b), reg("OUT", b), reg("ACC", b), lay.ksk_ptr(t), 0)
+                                for b in range(B) for t in mine if want(t)]))
         else:
             for r in self.chunk_order():
-                if r != lay.rank:
-                    self.comm.wait(m, r)
-                m.run_vp_multi([(self.pc2[t, r], reg("S", b), reg("OUT", b), reg("ACC", b), lay.ksk_ptr(t), 0)
-                                for b in range(B) for t in mine if want(t)])
+                if r != lay.rank or self.lockstep:
+                    ops.append(("wait", r))
+                ops.append(("run", [(self.pc2[t, r], reg("S", b), reg("OUT", b), reg("ACC", b), lay.ksk_ptr(t), 0)
+                                    for b in range(B) for t in mine if want(t)]))
         for r in range(lay.world):
             ks = [t - prm.L for t in lay.owned(r) if t >= prm.L]
             if ks:
-                self.comm.broadcast(m, lay.ACC + lay.T_off + 2 * ks[0] * rp, 2 * len(ks) * rp, r, B, lay.ACC_size)
-        self.comm.wait(m, -2)
+                ops.append(("broadcast", lay.ACC + lay.T_off + 2 * ks[0] * rp, 2 * len(ks) * rp, r, B, lay.ACC_size))
+        ops.append(("wait", -2))
         src1 = "S" if lay.kind == "rotate" else "IN"
-        m.run_vp_multi([(self.pc3[i], reg("ACC", b), reg(src1, b), reg("OUT", b), 0, 0)
-                        for b in range(B) for i in mine if i < prm.L and want(i)])
+        ops.append(("run", [(self.pc3[i], reg("ACC", b), reg(src1, b), reg("OUT", b), 0, 0)
+                            for b in range(B) for i in mine if i < prm.L and want(i)]))
+        return ops
+
+    def execute(self, ops):
+        m, comm = self.machine, self.comm
+        for op in ops:
+            if op[0] == "run":
+                if op[1]:
+                    m.run_vp_multi(op[1])
+            elif op[0] == "all_gather":
+                comm.all_gather(m, *op[1:])
+            elif op[0] == "broadcast":
+                comm.broadcast(m, *op[1:])
+            else:
+                comm.wait(m, op[1])
+
+    def run(self, galois_k: int = 1, only: list[int] | None = None):
+        self.execute(self.program(galois_k, only))
 
     def read_output(self, i: int, b: int = 0):
         lay, rp, L = self.lay, self.lay.prm.rp, self.lay.prm.L
         out = lay.region("OUT", b)
         return (self.machine.dma_mem_d2h(out + i * rp, lay.prm.n), self.machine.dma_mem_d2h(out + (L + i) * rp, lay.prm.n))
+
+
+def run_local_group(switches: list["KeySwitch"], group, galois_k: int = 1, only=None):
+    """One process driving every machine of a local group (aloha_group_create_local): the ranks' op lists are
+    walked in lockstep -- run ops go to each machine, every collective is issued once for the whole group."""
+    progs = [ks.program(galois_k, only) for ks in switches]
+    assert len({len(p) for p in progs}) == 1
+    for step in zip(*progs):
+        kind = step[0][0]
+        assert all(op[0] == kind for op in step)
+        if kind == "run":
+            for ks, op in zip(switches, step):
+                if op[1]:
+                    ks.machine.run_vp_multi(op[1])
+        elif kind == "all_gather":
+            group.all_gather_rows(*step[0][1:5], chunked=step[0][5])
+        elif kind == "broadcast":
+            _, row, nrows, root, count, stride = step[0]
+            for c in range(count):
+                group.broadcast_rows(row + c * stride, nrows, root)
+        else:
+            group.wait(step[0][1])                  # overlap: the switches were built with lockstep=True
+
+
+def write_replay_case(directory: str, switches: list["KeySwitch"], engine_cfg: dict, loads, dumps, galois_k: int = 1,
+                      only=None):
+    """Everything the C replay tool (aloha_b200/csrc/group_replay_main.cpp -- a caller that knows only
+    include/aloha_b200.h) needs to run this key-switch without Python: per rank r
+        rank<r>.cfg    vlmax_bits spm_rows ksk_rows pool_buffers isram_depth nmoduli, then q psi per modulus
+        rank<r>.isram  the instruction ROM image, n x 12 bytes
+        rank<r>.prog   one op per line: run <ncalls> then ncalls lines "pc src0 src1 rslt ksk step";
+                       allgather row rows_per_rank count stride chunked; bcast row nrows root; wait source
+        rank<r>.io     "spm|ksk <row> <file>" loads and "dump <row> <nwords> <file>" read-backs (raw u64 files)
+    loads[r] = [(space, row, array)], dumps[r] = [(row, nwords, name)]."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+    for r, ks in enumerate(switches):
+        m = ks.machine                     # a recorder: anything that kept the load_isram calls
+        with open(os.path.join(directory, f"rank{r}.cfg"), "w") as f:
+            mods = engine_cfg["moduli"]
+            f.write(f"{engine_cfg['vlmax_bits']} {ks.lay.spm_rows} {max(ks.lay.ksk_rows, 1)} {engine_cfg.get('pool_buffers', 0)} "
+                    f"{engine_cfg.get('isram_depth', 0)} {len(mods)}\n")
+            for q, psi in mods:
+                f.write(f"{q} {psi}\n")
+        rom = np.zeros((ks.pc_end, 12), dtype=np.uint8)
+        for words, pc in m.isram_loads:
+            rom[pc:pc + len(words)] = words
+        rom.tofile(os.path.join(directory, f"rank{r}.isram"))
+        with open(os.path.join(directory, f"rank{r}.prog"), "w") as f:
+            for op in ks.program(galois_k, only):
+                if op[0] == "run":
+                    f.write(f"run {len(op[1])}\n")
+                    for c in op[1]:
+                        f.write(" ".join(str(v) for v in c) + "\n")
+                elif op[0] == "all_gather":
+                    f.write(f"allgather {op[1]} {op[2]} {op[3]} {op[4]} {int(op[5])}\n")
+                elif op[0] == "broadcast":
+                    for c in range(op[4]):
+                        f.write(f"bcast {op[1] + c * op[5]} {op[2]} {op[3]}\n")
+                else:
+                    f.write(f"wait {op[1]}\n")
+        with open(os.path.join(directory, f"rank{r}.io"), "w") as f:
+            for n_, (space, row, arr) in enumerate(loads[r]):
+                name = f"rank{r}.in{n_}.u64"
+                np.ascontiguousarray(arr, dtype=np.uint64).tofile(os.path.join(directory, name))
+                f.write(f"{space} {row} {name}\n")
+            for row, nwords, name in dumps[r]:
+                f.write(f"dump {row} {nwords} {name}\n")
+
+
+class Recorder:
+    """A machine that only records what a KeySwitch loads into it (for write_replay_case)."""
+
+    def __init__(self):
+        self.isram_loads, self.loads = [], []
+
+    def load_isram(self, words, pc):
+        self.isram_loads.append((np.array(words), pc))
+
+    def dma_mem_h2d(self, row, data):
+        self.loads.append(("spm", row, np.array(data, dtype=np.uint64).reshape(-1)))
+
+    def dma_ksk_h2d(self, row, data):
+        self.loads.append(("ksk", row, np.array(data, dtype=np.uint64).reshape(-1)))
 
 
 # ------------------------------------------------------------------------------------------------ rescale

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstring>
 #include <set>
+#include <type_traits>
 #include <vector>
 
 #include "../../aloha_b200/csrc/aut_plan.hpp"
@@ -37,41 +38,54 @@ int aut_model_apply(uint32_t n, u64 k, u64 q, const u64 *src, u64 *dst, u64 stat
         const uint32_t slots = 1u << (T.log_jb + T.log_fb);
         if (slots > kAutTile) return -1;
         std::vector<u64> smem(kAutSmemWords, ~0ull);
-        for (int phase = 0; phase < 2; ++phase)
+        // per warp instruction: the lanes' accesses.  phase 0 = load (AutLoadWalk), 1 = store (AutStoreWalk),
+        // each thread walking its 8 slots exactly as the kernel does (incremental indices).
+        struct Access { bool valid; uint32_t i, d, sm; };
+        for (int phase = 0; phase < 2; ++phase) {
+            std::vector<std::vector<Access>> acc(kAutThreads, std::vector<Access>(8));
+            for (uint32_t tid = 0; tid < kAutThreads; ++tid) {
+                auto walk = [&](auto w) {
+                    for (int it = 0; it < 8; ++it) {
+                        Access a{!w.idle() && w.valid(), w.i, 0, w.sm};
+                        if constexpr (std::is_same_v<decltype(w), AutStoreWalk<true>> || std::is_same_v<decltype(w), AutStoreWalk<false>>) a.d = w.d;
+                        acc[tid][it] = a;
+                        w.next();
+                    }
+                };
+                if (phase == 0) { if (T.log_jb > 8) walk(AutLoadWalk<true>(P, T, tid)); else walk(AutLoadWalk<false>(P, T, tid)); }
+                else { if (T.log_fb > 8) walk(AutStoreWalk<true>(P, T, tid)); else walk(AutStoreWalk<false>(P, T, tid)); }
+            }
             for (int it = 0; it < 8; ++it)
                 for (uint32_t warp = 0; warp < 8; ++warp) {
                     std::set<uint32_t> sectors;
                     uint32_t bank[2][16] = {};
                     bool active = false;
                     for (uint32_t lane = 0; lane < 32; ++lane) {
-                        const uint32_t s = it * 256 + warp * 32 + lane;
-                        uint32_t jl, fl;
-                        if (phase == 0) aut_load_slot(T, s, &jl, &fl); else aut_store_slot(T, s, &jl, &fl);
-                        if (!(s < slots && jl < T.jcount && fl < T.fcount)) continue;
+                        const Access &a = acc[warp * 32 + lane][it];
+                        if (!a.valid) continue;
                         active = true;
-                        const uint32_t i = aut_src(P, T, jl, fl), d = aut_dst(P, T, jl, fl), w = fl * T.stride + jl;
-                        if (w >= kAutSmemWords) return -2;
-                        if (w + 1 > stats[4]) stats[4] = w + 1;
-                        ++bank[lane >> 4][w & 15];
+                        if (a.sm >= kAutSmemWords) return -2;
+                        if (a.sm + 1 > stats[4]) stats[4] = a.sm + 1;
+                        ++bank[lane >> 4][a.sm & 15];
                         if (phase == 0) {
-                            smem[w] = src[i];
-                            sectors.insert(i >> 2);
+                            smem[a.sm] = src[a.i];
+                            sectors.insert(a.i >> 2);
                         } else {
-                            const bool neg = (((u64)i * k2) & (2ull * n - 1)) >= n;
-                            dst[d] = neg ? q - smem[w] : smem[w];
-                            if (seen[d]) ++stats[1];
-                            seen[d] = 1;
+                            dst[a.d] = aut_negated(a.i, (uint32_t)k2, n) ? q - smem[a.sm] : smem[a.sm];
+                            if (seen[a.d]) ++stats[1];
+                            seen[a.d] = 1;
                             ++stats[0];
-                            sectors.insert(d >> 2);
+                            sectors.insert(a.d >> 2);
                         }
                     }
                     if (!active) continue;
                     ++stats[7];
                     stats[2 + phase] += sectors.size();
                     for (int h = 0; h < 2; ++h)
-                        for (int b = 0; b < 16; ++b)
-                            if (bank[h][b] > stats[5 + phase]) stats[5 + phase] = bank[h][b];
+                        for (int bnk = 0; bnk < 16; ++bnk)
+                            if (bank[h][bnk] > stats[5 + phase]) stats[5 + phase] = bank[h][bnk];
                 }
+        }
     }
     return 0;
 }
