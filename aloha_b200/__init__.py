@@ -66,7 +66,8 @@ EXPORTS = ["aloha_create", "aloha_destroy", "aloha_strerror", "aloha_last_error"
            "aloha_get_stats", "aloha_get_csr", "aloha_decode", "aloha_host_create",
            "aloha_host_destroy", "aloha_host_num_ops", "aloha_host_dram_write", "aloha_host_dram_read",
            "aloha_host_set_encoder_output", "aloha_host_run_op", "aloha_write_dump_text",
-           "aloha_flush", "aloha_group_unique_id", "aloha_group_create", "aloha_group_create_local",
+           "aloha_flush", "aloha_pinned_alloc", "aloha_pinned_free", "aloha_host_run_op_async", "aloha_host_sync",
+           "aloha_group_unique_id", "aloha_group_create", "aloha_group_create_local",
            "aloha_group_destroy", "aloha_group_size", "aloha_group_rank", "aloha_group_last_error",
            "aloha_group_all_gather_rows", "aloha_group_broadcast_rows", "aloha_group_wait"]
 
@@ -120,6 +121,10 @@ def load_library(rebuild: bool = False) -> C.CDLL:
         "aloha_host_run_op": (C.c_int, [vp, u32, p64, p8, p64, p8, C.POINTER(C.c_int)]),
         "aloha_write_dump_text": (C.c_int, [C.c_char_p, p64, p8, u64]),
         "aloha_flush": (C.c_int, [vp]),
+        "aloha_pinned_alloc": (C.c_int, [u64, C.POINTER(vp)]),
+        "aloha_pinned_free": (None, [vp]),
+        "aloha_host_run_op_async": (C.c_int, [vp, u32, p64, p8, p64, p8, C.POINTER(C.c_int)]),
+        "aloha_host_sync": (C.c_int, [vp]),
         "aloha_group_unique_id": (C.c_int, [p8]),
         "aloha_group_create": (C.c_int, [vp, p8, C.c_int, C.c_int, C.POINTER(vp)]),
         "aloha_group_create_local": (C.c_int, [C.POINTER(vp), C.c_int, C.POINTER(vp)]),
@@ -423,6 +428,32 @@ class HostDriver:
         if has_sub.value:
             out.append((0, sub, swr.astype(bool)))
         out.append((None, dump, wr.astype(bool)))
+        return out
+
+    def run_all_async(self, first: int = 0, count: int | None = None):
+        """Ops [first, first+count) with every dump the testbench would write, read-backs overlapped with the
+        following ops, one synchronisation at the end.  -> per op, the same list run_op returns."""
+        count = len(self) - first if count is None else count
+        w = 4 * self.n
+        res = []
+        for i in range(first, first + count):
+            dump, sub = np.empty(w, np.uint64), np.empty(w, np.uint64)
+            wr, swr = np.empty(w, np.uint8), np.empty(w, np.uint8)
+            has_sub = C.c_int(0)
+            rc = self.L.aloha_host_run_op_async(self.h, i, _p64(dump), _p8(wr), _p64(sub), _p8(swr), C.byref(has_sub))
+            if rc:
+                raise AlohaError(rc, f"host_run_op_async({i})", self.L.aloha_last_error(self.eng.h).decode())
+            res.append((has_sub.value, dump, wr, sub, swr))
+        rc = self.L.aloha_host_sync(self.h)
+        if rc:
+            raise AlohaError(rc, "host_sync", self.L.aloha_last_error(self.eng.h).decode())
+        out = []
+        for has_sub, dump, wr, sub, swr in res:
+            ops = []
+            if has_sub:
+                ops.append((0, sub, swr.astype(bool)))
+            ops.append((None, dump, wr.astype(bool)))
+            out.append(ops)
         return out
 
     @staticmethod

@@ -966,13 +966,31 @@ void commit(aloha *E, const Plan &plan) {
     E->stats.ops_fused += plan.fused;
 }
 
+// Events are recycled: creating and destroying one per DMA call costs more than the call's own enqueue.
+int get_event(aloha *E, cudaEvent_t *ev) {
+    if (!E->event_pool.empty()) { *ev = E->event_pool.back(); E->event_pool.pop_back(); return ALOHA_OK; }
+    CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    return ALOHA_OK;
+}
+void put_event(aloha *E, cudaEvent_t ev) { E->event_pool.push_back(ev); }
+// `waiter` waits for everything queued on `signaller` so far
+int order_after(aloha *E, cudaStream_t waiter, cudaStream_t signaller) {
+    cudaEvent_t ev;
+    int rc = get_event(E, &ev);
+    if (rc) return rc;
+    CU(cudaEventRecord(ev, signaller));
+    CU(cudaStreamWaitEvent(waiter, ev, 0));
+    put_event(E, ev);           // the wait has captured the event's current record; re-recording later is safe
+    return ALOHA_OK;
+}
+
 // Work about to be queued on `st` writes SPM words [off, off+n): it must not overtake a pending
 // asynchronous download of overlapping rows.
 int wait_for_downloads(aloha *E, cudaStream_t st, u64 off, u64 n) {
     for (size_t i = 0; i < E->pending_down.size();) {
         auto &p = E->pending_down[i];
         if (cudaEventQuery(p.done) == cudaSuccess) {
-            cudaEventDestroy(p.done);
+            put_event(E, p.done);
             E->pending_down.erase(E->pending_down.begin() + i);
             continue;
         }
@@ -1195,6 +1213,7 @@ void aloha_destroy(aloha_t *E) {
     if (E->up_stream) { cudaStreamSynchronize(E->up_stream); cudaStreamDestroy(E->up_stream); }
     if (E->down_stream) { cudaStreamSynchronize(E->down_stream); cudaStreamDestroy(E->down_stream); }
     for (auto &p : E->pending_down) cudaEventDestroy(p.done);
+    for (auto ev : E->event_pool) cudaEventDestroy(ev);
     delete E;
 }
 
@@ -1251,20 +1270,15 @@ int aloha_dma_mem_h2d_async(aloha_t *E, uint32_t row, const uint64_t *src, uint6
         CU(cudaStreamCreateWithFlags(&E->down_stream, cudaStreamNonBlocking));
     }
     // the upload must not overtake kernels already queued (they may still read these rows) ...
-    cudaEvent_t ev;
-    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CU(cudaEventRecord(ev, E->stream));
-    CU(cudaStreamWaitEvent(E->up_stream, ev, 0));
-    CU(cudaEventDestroy(ev));
+    rc = order_after(E, E->up_stream, E->stream);
+    if (rc) return rc;
     // ... nor a pending download of overlapping rows
     rc = wait_for_downloads(E, E->up_stream, off, n);
     if (rc) return rc;
     CU(cudaMemcpyAsync(E->d_spm + off, src, bytes, cudaMemcpyHostToDevice, E->up_stream));
     // every later run_vp sees the data
-    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CU(cudaEventRecord(ev, E->up_stream));
-    CU(cudaStreamWaitEvent(E->stream, ev, 0));
-    CU(cudaEventDestroy(ev));
+    rc = order_after(E, E->stream, E->up_stream);
+    if (rc) return rc;
     mark_written(E, off, n);
     return ALOHA_OK;
 }
@@ -1279,14 +1293,12 @@ int aloha_dma_mem_d2h_async(aloha_t *E, uint64_t *dst, uint32_t row, uint64_t by
         CU(cudaStreamCreateWithFlags(&E->up_stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&E->down_stream, cudaStreamNonBlocking));
     }
-    cudaEvent_t ev;
-    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CU(cudaEventRecord(ev, E->stream));                // sees every run_vp issued so far
-    CU(cudaStreamWaitEvent(E->down_stream, ev, 0));
-    CU(cudaEventDestroy(ev));
+    int rc = order_after(E, E->down_stream, E->stream);     // sees every run_vp issued so far
+    if (rc) return rc;
     CU(cudaMemcpyAsync(dst, E->d_spm + off, bytes, cudaMemcpyDeviceToHost, E->down_stream));
     aloha::PendingDma p{off, n, nullptr};
-    CU(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
+    rc = get_event(E, &p.done);
+    if (rc) return rc;
     CU(cudaEventRecord(p.done, E->down_stream));
     // later work that WRITES these rows waits for this event (wait_for_downloads); everything else
     // keeps running beside the copy
@@ -1369,10 +1381,16 @@ int aloha_sync(aloha_t *E) {
         CU(cudaStreamSynchronize(E->up_stream));
         CU(cudaStreamSynchronize(E->down_stream));
     }
-    for (auto &p : E->pending_down) cudaEventDestroy(p.done);
+    for (auto &p : E->pending_down) put_event(E, p.done);
     E->pending_down.clear();
     return ALOHA_OK;
 }
+
+int aloha_pinned_alloc(uint64_t bytes, void **out) {
+    if (!out || !bytes) return ALOHA_E_ARG;
+    return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? ALOHA_OK : ALOHA_E_NOMEM;
+}
+void aloha_pinned_free(void *p) { if (p) cudaFreeHost(p); }
 
 int aloha_flush(aloha_t *E) {
     if (!E) return ALOHA_E_ARG;

@@ -103,6 +103,7 @@ struct aloha {
     cudaStream_t up_stream = nullptr, down_stream = nullptr;   // asynchronous DMA channels
     struct PendingDma { alb::u64 off, n; cudaEvent_t done; };
     std::vector<PendingDma> pending_down;                      // downloads not yet known complete
+    std::vector<cudaEvent_t> event_pool;                       // recycled (timing-disabled) events
     std::vector<uint32_t> queued_pcs;                          // ALOHA_F_DEFER: run_vp calls not yet planned
     std::vector<aloha_vp_args> queued_args;
     alb::u64 *d_spm = nullptr, *d_ksk = nullptr, *d_pool = nullptr;

@@ -201,6 +201,8 @@ def run_gpu(args):
         torch.cuda.set_stream(stream)
 
         def timed0(fn, steps):
+            if world > 1:
+                dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -208,9 +210,13 @@ def run_gpu(args):
                 fn()
             e1.record(stream)
             torch.cuda.synchronize()
-            return e0.elapsed_time(e1)
+            ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item())
         if args.only == "keyswitch":
-            out = measure_keyswitch(torch, dist, A, {"device": local}, stream, timed0, world, rank)
+            out = measure_keyswitch(torch, dist, A, {"device": local}, stream, timed0, world, rank,
+                                    shapes=args.shapes.split(",") if args.shapes else None)
         elif args.only == "tv":
             out = measure_tv_latency(A) if rank == 0 else None
         elif args.only == "rotmac_gather":
@@ -446,29 +452,37 @@ def measure_tv_latency(A):
                 host.set_encoder_output(int(i), pool[key])
             eng.sync()
             run = host.run_op if dumps else host.run_op_nodump
+
+            def one_pass():
+                if dumps == "async":          # every dump the testbench writes, read-backs overlapped
+                    host.run_all_async()
+                else:
+                    for i in range(len(host)):
+                        run(i)
+                    eng.sync()
             t0 = time.perf_counter()
-            for i in range(len(host)):
-                run(i)
-            eng.sync()
+            one_pass()
             dt = time.perf_counter() - t0
             best = 1e9
             for _ in range(5):                # later passes: plans are cached (steady state)
                 t1 = time.perf_counter()
-                for i in range(len(host)):
-                    run(i)
-                eng.sync()
+                one_pass()
                 best = min(best, time.perf_counter() - t1)
             st = eng.stats()
             eng.close()
             return dt, best, st
         first, steady, st = gpu_once()
+        _, steady_async, _ = gpu_once(dumps="async")
         _, steady_nodump, _ = gpu_once(dumps=False)
         _, steady_graphs, _ = gpu_once(flags=A.F_GRAPHS, dumps=False)
         out[case] = {"ops": len(prog_lines), "gpu_ms_first_run": 1e3 * first, "gpu_ms_steady": 1e3 * steady,
+                     "gpu_ms_steady_async_dumps": 1e3 * steady_async,
                      "gpu_ms_steady_no_dumps": 1e3 * steady_nodump, "gpu_ms_steady_no_dumps_cuda_graphs": 1e3 * steady_graphs,
                      "kernel_launches_per_pass": st["kernel_launches"] / 6.0,
-                     "note": "gpu_ms_steady includes every per-op DMA and the 256 KiB dump read-back the testbench does "
-                             "after each op; the no_dumps figures run the same ops with one sync at the end"}
+                     "note": "gpu_ms_steady includes every per-op DMA and the blocking 256 KiB dump read-back the testbench does "
+                             "after each op; gpu_ms_steady_async_dumps produces the same dumps through aloha_host_run_op_async "
+                             "(read-backs on the download channel, one sync at the end; includes the Python-side allocation of "
+                             "the dump arrays); the no_dumps figures run the same ops with one sync at the end"}
     # cpu_baseline leg: the same replays on the oracle, one thread
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import golden_util as G
@@ -570,85 +584,137 @@ def measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, polys
     return out
 
 
-def measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank, L=47):
-    """BASELINE.json configs[4]: limb-sharded key-switch stream, N = 2^16, L + 1 = 48 limbs."""
-    from aloha_b200 import keyswitch as KS, params
-    pr = params.synthetic_primes(L + 1, 2 * N)
-    P, q = pr[0], pr[1:]
-    psi = [params.min_primitive_root(p, 2 * N) for p in q + [P]]
-    lay = KS.KeySwitchLayout(N, q, P, world, rank)
-    eng = A.Engine(vlmax_bits=N * 64, spm_rows=lay.spm_rows, ksk_rows=lay.ksk_rows,
-                   moduli=list(zip(q + [P], psi)), pool_buffers=6144, isram_depth=32768,
-                   flags=int(os.environ.get("ALOHA_BENCH_KS_FLAGS", "0")), **eng_kwargs)
-    eng.set_stream(stream.cuda_stream)
-    comm = KS.TorchComm() if world > 1 else KS.LocalComm()
-    ks = KS.ShardedKeySwitch(eng, lay, comm)
-    def limb_data(i):          # any rank can regenerate any limb's inputs
-        rng = np.random.default_rng(1000 + i)
-        m = lay.modulus(i)
-        return (rng.integers(0, m, N, dtype=np.uint64), rng.integers(0, m, N, dtype=np.uint64),
-                rng.integers(0, m, 2 * L * N, dtype=np.uint64))
+KS_SHAPES = [
+    # name, L, K, dnum, batch
+    ("digit_1_limb", 47, 1, 47, 1),      # the reference kernel's shape (one limb per digit, K = 1) at 48 limbs
+    ("dnum5_k8", 40, 8, 5, 1),           # a hybrid shape real schemes use: 5 digits of 8 limbs, 8 special primes
+    ("dnum5_k8_batch8", 40, 8, 5, 8),    # the same, eight key-switches side by side (launches fill the GPUs)
+]
 
-    def fill(target, layout):
-        for i in layout.owned():
-            a, b, key = limb_data(i)
-            if i < L:
-                target.load_input(i, a, b)
-            target.load_ksk(i, key)
-    fill(ks, lay)
-    k = pow(3, 2, 2 * N)
-    for _ in range(2):
-        ks.run(k)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(4):
-        ks.run(k)
-    torch.cuda.synchronize()
-    extra = torch.tensor([int(0.4 / max((time.perf_counter() - t0) / 4, 1e-4))], device="cuda")
-    if world > 1:                              # same count on every rank (see the main warm-up)
-        dist.all_reduce(extra, op=dist.ReduceOp.MAX)
-    for _ in range(int(extra.item())):
-        ks.run(k)
-    s0 = eng.stats()
-    steps = 20
-    ms = timed(lambda: ks.run(k), steps)
-    s1 = eng.stats()
-    ms_comm = None
-    if world > 1:
-        def only_comm():
-            comm.all_gather_digits(ks)
-            comm.broadcast_t(ks)
-        only_comm()
-        ms_comm = timed(only_comm, steps) / steps
-    sharded_ok = None
-    if world > 1:
-        # every rank re-runs the whole stream alone (no collective) and compares its own output limbs
-        ks.run(k)
-        mine = {i: ks.read_output(i) for i in lay.owned() if i < L}
+
+def measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank, shapes=None):
+    """BASELINE.json configs[4]: limb-sharded key-switch streams, N = 2^16, 48 limbs, generated by
+    aloha_b200.hks; NCCL inside the C library (aloha_group_*), transfers overlapped with phase 2.
+    Every rank checks output limbs of its own against the oracle (>= 4 limbs over the whole job)."""
+    from aloha_b200 import hks, params
+    from oracle import oracle as O
+    peak, _ = peaks()
+    out = {}
+    grp = None
+    for name, L, K, dnum, batch in KS_SHAPES:
+        if shapes and name not in shapes:
+            continue
+        primes = params.synthetic_primes(L + K, 2 * N)
+        p, q = primes[:K], primes[K:]
+        psi = {m: params.min_primitive_root(m, 2 * N) for m in primes}
+        prm = hks.Params(N, q, p, dnum)
+        lay = hks.Layout(prm, world, rank, batch)
+        eng = A.Engine(vlmax_bits=N * 64, spm_rows=lay.spm_rows, ksk_rows=max(lay.ksk_rows, 1),
+                       moduli=[(m, psi[m]) for m in prm.moduli], pool_buffers=min(32768, max(2048, 4 * batch * lay.per_rank * (prm.dnum * (4 if prm.alpha > 1 else 1) + 8))),
+                       isram_depth=1 << 17,
+                       flags=int(os.environ.get("ALOHA_BENCH_KS_FLAGS", "0")), **eng_kwargs)
+        eng.set_stream(stream.cuda_stream)
+        if world > 1:
+            uid = [A.Group.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            grp = A.Group.create(eng, uid[0], rank, world)
+            comm = hks.GroupComm(grp)
+        else:
+            comm = hks.LocalComm()
+        overlap = world > 1 and not os.environ.get("ALOHA_BENCH_KS_NO_OVERLAP")
+        ks = hks.KeySwitch(eng, lay, comm, overlap=overlap)
+
+        def limb_inputs(i, b=0):      # any rank can regenerate any limb's inputs
+            rng = np.random.default_rng(1000 + 64 * b + i)
+            return rng.integers(0, prm.q[i], N, dtype=np.uint64), rng.integers(0, prm.q[i], N, dtype=np.uint64)
+
+        def modulus_key(t):
+            rng = np.random.default_rng(5000 + t)
+            return rng.integers(0, prm.moduli[t], 2 * prm.dnum * N, dtype=np.uint64)
+        for t in lay.owned():
+            if t < L:
+                for b in range(batch):
+                    ks.load_input(t, limb_inputs(t, b), b)
+            ks.load_ksk(t, modulus_key(t))
+        k = pow(3, 18, 2 * N) & (N - 1)            # a pseudo-random permutation (vlmax = N keeps log2 N bits of k)
+        prog = ks.program(k)
+        for _ in range(2):
+            ks.execute(prog)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            ks.execute(prog)
+        torch.cuda.synchronize()
+        extra = torch.tensor([int(0.3 / max((time.perf_counter() - t0) / 4, 1e-4))], device="cuda")
+        if world > 1:                              # same count on every rank (see the main warm-up)
+            dist.all_reduce(extra, op=dist.ReduceOp.MAX)
+        for _ in range(int(extra.item())):
+            ks.execute(prog)
+        s0 = eng.stats()
+        steps = 20
+        ms = timed(lambda: ks.execute(prog), steps)
+        s1 = eng.stats()
+        # the same stream with the transfers left out (results are meaningless, the kernels are the same):
+        # what is left of the transfers after overlap = ms - ms_compute
+        ms_compute = None
+        if world > 1:
+            compute_only = [op for op in prog if op[0] == "run"]
+            ks.execute(compute_only)
+            ms_compute = timed(lambda: ks.execute(compute_only), steps) / steps
+        # per-phase device time of one key-switch (each phase timed alone, transfers excluded)
+        runs = [op for op in prog if op[0] == "run" and op[1]]
+        phase_ms = []
+        for op in runs:
+            ks.execute([op])
+            phase_ms.append(timed(lambda op=op: ks.execute([op]), 10) / 10)
+        # parity at full size: output limbs of this rank against the oracle
+        ks.execute(prog)
+        mine = [i for i in lay.owned() if i < L]
+        check = mine[:: max(1, len(mine) // max(1, -(-4 // world)))][: max(1, -(-4 // world))]
+        ok = True
+        if check:
+            lay1 = hks.Layout(prm)
+            om = O.GoldenModel(vlmax_bits=N * 64, spm_rows=lay1.spm_rows, ksk_rows=lay1.ksk_rows, moduli=[(m, psi[m]) for m in prm.moduli])
+            oks = hks.KeySwitch(om, lay1)
+            for i in range(L):
+                oks.load_input(i, limb_inputs(i, batch - 1))
+            for t in set(check) | set(range(L, L + K)):
+                oks.load_ksk(t, modulus_key(t))
+            oks.run(k, only=check)
+            for i in check:
+                want, got = oks.read_output(i), ks.read_output(i, batch - 1)
+                ok = ok and bool((want[0] == got[0]).all() and (want[1] == got[1]).all())
+            del oks, om
+        flag = torch.tensor([1 if ok else 0, len(check)], device="cuda")
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.SUM)
+        all_ok = bool(flag[0].item() == world)
+        tcount = prm.transform_count()
+        alg_bytes = (2 * prm.dnum * (L + K) + 2 * tcount + L) * N * 8 * batch - (batch - 1) * 2 * prm.dnum * (L + K) * N * 8
+        per_s = batch * steps / (ms / 1e3)
+        res = {"value": per_s, "unit": "key-switches/s", "ms_per_step": ms / steps, "ms_per_keyswitch": ms / steps / batch,
+               "limbs": L + K, "special_primes": K, "dnum": prm.dnum, "alpha": prm.alpha, "batch": batch,
+               "limb_ntts_per_keyswitch": tcount, "limb_ntts_per_s": tcount * per_s,
+               "phase_ms": phase_ms, "launches_per_step_per_rank": (s1["kernel_launches"] - s0["kernel_launches"]) / steps,
+               "plans_built_in_timed_region": s1["plans_built"] - s0["plans_built"],
+               "ops_fused_per_step": (s1["ops_fused"] - s0["ops_fused"]) / steps,
+               "transfers": None if world == 1 else {
+                   "backend": "NCCL inside libaloha_b200.so (aloha_group_*), communication stream per GPU",
+                   "all_gather_bytes": lay.slots * N * 8 * batch, "broadcast_bytes": 2 * K * N * 8 * batch,
+                   "overlapped_with_phase2": overlap, "ms_compute_only": ms_compute,
+                   "ms_exposed": ms / steps - ms_compute},
+               "output_limbs_checked_against_oracle": int(flag[1].item()), "checked_against_oracle": all_ok,
+               "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,
+                            "algorithmic_bytes_per_step": alg_bytes,
+                            "algorithmic_bytes_are": "the key (2 dnum (L+K) polynomials, read once per step) + 2 N 8 per limb-(I)NTT + the gathered digits",
+                            "achieved": alg_bytes / world / (ms / steps / 1e3) / 1e9,
+                            "frac": alg_bytes / world / (ms / steps / 1e3) / 1e9 / peak}}
+        out[name] = res
+        if grp is not None:
+            grp.close()
+            grp = None
         eng.close()
-        lay1 = KS.KeySwitchLayout(N, q, P, 1, 0)
-        eng1 = A.Engine(vlmax_bits=N * 64, spm_rows=lay1.spm_rows, ksk_rows=lay1.ksk_rows,
-                        moduli=list(zip(q + [P], psi)), pool_buffers=6144, isram_depth=32768, **eng_kwargs)
-        eng1.set_stream(stream.cuda_stream)
-        ks1 = KS.ShardedKeySwitch(eng1, lay1, KS.LocalComm())
-        fill(ks1, lay1)
-        ks1.run(k)
-        ok = all((ks1.read_output(i)[0] == v[0]).all() and (ks1.read_output(i)[1] == v[1]).all() for i, v in mine.items())
-        eng1.close()
-        flag = torch.tensor([1 if ok else 0], device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        sharded_ok = bool(flag.item())
-    else:
-        eng.close()
-    return {"value": steps / (ms / 1e3), "unit": "key-switches/s", "ms_per_keyswitch": ms / steps,
-            "limbs": L + 1, "limb_ntts_per_keyswitch": KS.transform_count(L),
-            "limb_ntts_per_s": KS.transform_count(L) * steps / (ms / 1e3),
-            "nccl_ms_per_keyswitch": ms_comm, "all_gather_bytes": lay.slots * N * 8,
-            "sharded_output_equals_single_gpu": sharded_ok,
-            "launches_per_keyswitch_per_rank": (s1["kernel_launches"] - s0["kernel_launches"]) / steps,
-            "plans_built_in_timed_region": s1["plans_built"] - s0["plans_built"],
-            "plans_reused_in_timed_region": s1["plans_reused"] - s0["plans_reused"],
-            "ops_fused_per_keyswitch": (s1["ops_fused"] - s0["ops_fused"]) / steps}
+    return out
 
 
 def main():
@@ -661,6 +727,7 @@ def main():
     ap.add_argument("--chunk-mib", type=int, default=0, help="override the engine's L2 chunk size")
     ap.add_argument("--polys", type=int, default=64)
     ap.add_argument("--no-extra", action="store_true", help="skip the rotate-MAC and key-switch workloads")
+    ap.add_argument("--shapes", default="", help="with --only keyswitch: comma-separated names from KS_SHAPES")
     ap.add_argument("--galois", default="", help="with --only rotmac: one Galois element by name, e.g. 3^18")
     ap.add_argument("--only", default="", choices=["", "keyswitch", "rotmac", "rotmac_gather", "tv"], help="profiling: run one extra workload alone")
     args = ap.parse_args()

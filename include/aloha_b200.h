@@ -148,6 +148,9 @@ int aloha_run_vp_batch(aloha_t *, uint32_t pc, uint32_t count, const aloha_vp_ar
  * per-modulus sections of a key-switch stream whose VSETQ immediates differ). */
 int aloha_run_vp_multi(aloha_t *, uint32_t count, const uint32_t *pcs, const aloha_vp_args *args);
 int aloha_sync(aloha_t *);
+/* Page-locked host memory for the asynchronous DMA channels (what a driver's DMA-buffer allocator hands out) */
+int aloha_pinned_alloc(uint64_t bytes, void **out);
+void aloha_pinned_free(void *);
 /* ALOHA_F_DEFER: plan and launch everything queued so far; does not wait for the device. */
 int aloha_flush(aloha_t *);
 
@@ -219,6 +222,13 @@ int aloha_host_set_encoder_output(aloha_host_t *, uint32_t op_index, const uint6
  * dump == NULL runs the op without the read-back (nothing is copied to the host, nothing blocks). */
 int aloha_host_run_op(aloha_host_t *, uint32_t op_index, uint64_t *dump, uint8_t *written,
                       uint64_t *sub_dump, uint8_t *sub_written, int *has_sub);
+/* PROGRAM-level scheduling: the same op without the blocking read-back the testbench does
+ * after every op (:600-632).  Dumps and store_cipher data are copied out by the download channel into a
+ * page-locked ring while later ops run; dump / sub_dump (and the modelled DDR) are valid after
+ * aloha_host_sync.  The written masks are filled in immediately. */
+int aloha_host_run_op_async(aloha_host_t *, uint32_t op_index, uint64_t *dump, uint8_t *written,
+                            uint64_t *sub_dump, uint8_t *sub_written, int *has_sub);
+int aloha_host_sync(aloha_host_t *);
 /* "%0d" per line, 'x' for never-written words (dump_poly, top_noaxilite_tb.sv:536-565) */
 int aloha_write_dump_text(const char *path, const uint64_t *data, const uint8_t *written,
                           uint64_t nwords);
