@@ -28,7 +28,7 @@ KSK_ROWS = 9216              # src/mem_buf/ksk_mem.sv:12-16
 REFERENCE_MODULI = ((576460825317867521, 3825716582911), (576460924102115329, 79932510954937),
                     (576462951330889729, 101017252977188))
 
-F_NO_BATCH, F_NO_ALIAS, F_GRAPHS, F_NO_FUSE, F_STRICT, F_DEFER, F_GENERIC_MODMUL, F_AUT_GATHER = 1, 2, 4, 8, 16, 32, 64, 128
+F_NO_BATCH, F_NO_ALIAS, F_GRAPHS, F_NO_FUSE, F_STRICT, F_DEFER, F_GENERIC_MODMUL, F_AUT_GATHER, F_AUT_TILED = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 _ERRORS = {-1: "E_ARG", -2: "E_RANGE", -3: "E_OPCODE", -4: "E_STATE", -5: "E_ILLEGAL", -6: "E_NOBREAK",
            -7: "E_UNDEFINED", -8: "E_CUDA", -9: "E_NOMEM"}

@@ -44,8 +44,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     subprocess.check_call([NVCC, "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
     # the C host program for limb-sharded cases: sees nothing but include/aloha_b200.h and the library
-    subprocess.check_call([os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", os.path.join(CSRC, "group_replay_main.cpp"),
-                           "-o", REPLAY, "-L" + HERE, "-l:" + os.path.basename(LIB), "-Wl,-rpath,$ORIGIN"])
+    if os.path.basename(LIB) == "libaloha_b200.so":     # (not for A/B variants built under another name)
+        subprocess.check_call([os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", os.path.join(CSRC, "group_replay_main.cpp"),
+                               "-o", REPLAY, "-L" + HERE, "-l:" + os.path.basename(LIB), "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 

@@ -38,7 +38,10 @@
 
 namespace alb {
 
-constexpr unsigned kAutTileLog = 11;                 // 2048 words = 16 KiB per tile
+#ifndef ALOHA_AUT_TILE_LOG
+#define ALOHA_AUT_TILE_LOG 11
+#endif
+constexpr unsigned kAutTileLog = ALOHA_AUT_TILE_LOG;  // 2048 words = 16 KiB per tile
 constexpr unsigned kAutTile = 1u << kAutTileLog;
 constexpr unsigned kAutSmemWords = kAutTile + 1024;  // worst-case padding: FB rows * 1 word (FB <= 1024)
 constexpr unsigned kAutThreads = 256;
@@ -48,6 +51,7 @@ struct AutClass {
     uint32_t gap;              // arc length
     uint32_t log_jb, log_fb;   // tile = 2^log_jb points x 2^log_fb offsets
     uint32_t fblocks;          // f-blocks per j-block
+    uint32_t fblocks_magic;    // ceil(2^32 / fblocks): tile / fblocks = umulhi(tile, magic) for tile < 2^16
     uint32_t stride;           // shared-memory row stride in words (row = one f)
     uint32_t tile_begin;       // first tile id of this class
 };
@@ -67,7 +71,7 @@ struct AutTile {
 ALOHA_HD AutTile aut_tile(const AutPlan &p, uint32_t tile) {
     const AutClass &c = p.cls[tile >= p.cls[1].tile_begin ? 1 : 0];
     tile -= c.tile_begin;
-    const uint32_t jb = tile / c.fblocks, fb = tile - jb * c.fblocks;
+    const uint32_t jb = c.fblocks == 1 ? tile : (uint32_t)(((uint64_t)tile * c.fblocks_magic) >> 32), fb = tile - jb * c.fblocks;
     AutTile t;
     t.log_jb = c.log_jb; t.log_fb = c.log_fb; t.stride = c.stride;
     t.j0 = c.j_begin + (jb << c.log_jb);
@@ -158,22 +162,19 @@ namespace autdetail {
 
 inline uint32_t clog2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) ++l; return l; }
 
-// tile shape and padding for a class of `count` points with arc `gap`
-inline void shape_class(AutClass &c) {
+// shape a class's tiles as 2^log_jb points x 2^log_fb offsets (clamped to what the class has) and pad the rows
+inline void shape_class(AutClass &c, uint32_t want_log_fb) {
     const uint32_t count = c.j_end - c.j_begin, lj = clog2(count ? count : 1), lf = clog2(c.gap ? c.gap : 1);
-    uint32_t log_jb, log_fb;
-    if (lj + lf <= kAutTileLog) { log_jb = lj; log_fb = lf; }
-    else {
-        log_fb = lf < 6 ? lf : 6;                        // prefer 64-word destination runs ...
-        log_jb = kAutTileLog - log_fb < lj ? kAutTileLog - log_fb : lj;
-        if (log_jb + log_fb < kAutTileLog)               // ... unless there are too few points: lengthen the f side
-            log_fb = kAutTileLog - log_jb < lf ? kAutTileLog - log_jb : lf;
-    }
+    uint32_t log_fb = want_log_fb < lf ? want_log_fb : lf;
+    uint32_t log_jb = kAutTileLog - log_fb < lj ? kAutTileLog - log_fb : lj;
+    if (log_jb + log_fb < kAutTileLog)                   // too few points: lengthen the f side
+        log_fb = kAutTileLog - log_jb < lf ? kAutTileLog - log_jb : lf;
     if (log_fb > 10) log_fb = 10;                        // shared-memory padding budget (kAutSmemWords)
     c.log_jb = log_jb;
     c.log_fb = log_fb;
     const uint32_t JB = 1u << log_jb, FB = 1u << log_fb;
     c.fblocks = c.gap ? (c.gap + FB - 1) / FB : 0;
+    c.fblocks_magic = c.fblocks > 1 ? (uint32_t)(((1ull << 32) + c.fblocks - 1) / c.fblocks) : 0;
     // row stride: the store phase reads element (jl, fl) with fl fastest; 16 consecutive lanes must fall on
     // 16 different 8-byte banks.  FB >= 16: an odd stride; 1 < FB < 16: stride = 16 / FB (mod 32 / FB).
     if (FB >= 16) c.stride = JB | 1;
@@ -189,17 +190,18 @@ inline uint32_t class_tiles(const AutClass &c) {
     return count && c.gap ? ((count + (1u << c.log_jb) - 1) >> c.log_jb) * c.fblocks : 0;
 }
 
-inline void finish(AutPlan &p) {
-    shape_class(p.cls[0]);
-    shape_class(p.cls[1]);
+inline void number_tiles(AutPlan &p) {
     p.cls[0].tile_begin = 0;
     p.cls[1].tile_begin = class_tiles(p.cls[0]);
     p.ntiles = p.cls[1].tile_begin + class_tiles(p.cls[1]);
 }
 
-// 32-byte sectors touched by the warp instructions of one tile (both phases) and the elements it holds
-inline void tile_cost(const AutPlan &p, uint32_t tile, uint64_t *sectors, uint64_t *elements, uint64_t *winstr) {
+// What one tile costs, in SM cycles (rough, but it ranks shapes the way the kernels behave): every warp
+// that has work in a phase issues about 25 instructions per slot step, and every 32-byte sector touched on
+// either side is memory-system work.  Replays the kernel's own walks.
+inline double tile_cost(const AutPlan &p, uint32_t tile, uint64_t *elements) {
     const AutTile t = aut_tile(p, tile);
+    uint64_t sectors = 0, warp_steps = 0;
     const uint32_t slots = 1u << (t.log_jb + t.log_fb);
     for (int phase = 0; phase < 2; ++phase)
         for (uint32_t base = 0; base < slots; base += 32) {
@@ -214,9 +216,45 @@ inline void tile_cost(const AutPlan &p, uint32_t tile, uint64_t *sectors, uint64
                 if (!dup) sec[ns++] = a;
                 if (phase == 0) ++*elements;
             }
-            *sectors += ns;
-            *winstr += ns ? 1 : 0;
+            sectors += ns;
+            warp_steps += ns ? 1 : 0;
         }
+    return 12.0 * (double)warp_steps + 1.4 * (double)sectors;
+}
+
+// cost per element of a class with its current shape: a full tile and the last (partial) f-block, weighted
+inline double class_cost(const AutPlan &p, int c) {
+    const AutClass &C = p.cls[c];
+    if (C.j_end == C.j_begin || !C.gap) return 0;
+    uint64_t el_full = 0, el_last = 0;
+    const double full = tile_cost(p, C.tile_begin, &el_full);
+    if (C.fblocks == 1) return full / (double)el_full;
+    const double last = tile_cost(p, C.tile_begin + C.fblocks - 1, &el_last);
+    return (full * (C.fblocks - 1) + last) / ((double)el_full * (C.fblocks - 1) + (double)el_last);
+}
+
+// choose each class's tile shape (destination-run length 8 .. 1024 words) by that cost
+inline double finish(AutPlan &p) {
+    double total = 0;
+    for (int c = 0; c < 2; ++c) {
+        AutClass best = p.cls[c];
+        double best_cost = -1;
+        uint32_t last_fb = ~0u;
+        for (uint32_t want = 3; want <= 10; ++want) {
+            shape_class(p.cls[c], want);
+            if (p.cls[c].log_fb == last_fb) continue;          // clamped to the same shape as before
+            last_fb = p.cls[c].log_fb;
+            number_tiles(p);
+            const double cost = class_cost(p, c);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = p.cls[c]; }
+        }
+        p.cls[c] = best;
+        number_tiles(p);
+        const double share = (double)(best.j_end - best.j_begin) * best.gap / ((double)p.mask + 1);
+        total += share * (best_cost < 0 ? 0 : best_cost);
+    }
+    number_tiles(p);
+    return total;
 }
 
 }  // namespace autdetail
@@ -229,28 +267,15 @@ inline AutPlan make_aut_plan(uint32_t n, uint64_t k) {
     uint64_t inv = k;                                   // Newton: k^-1 mod 2^64
     for (int i = 0; i < 6; ++i) inv *= 2 - k * inv;
     base.kinv = (uint32_t)(inv & (n - 1));
+    double built_cost = 0;
     auto build = [&](uint64_t u, uint64_t alpha, uint64_t v, uint64_t beta) {
         AutPlan p = base;
         p.cls[0].j_begin = 0; p.cls[0].j_end = (uint32_t)v; p.cls[0].gap = (uint32_t)alpha;
         p.cls[1].j_begin = (uint32_t)v; p.cls[1].j_end = (uint32_t)(u + v); p.cls[1].gap = (uint32_t)beta;
-        autdetail::finish(p);
+        built_cost = autdetail::finish(p);       // per-class tile shapes chosen by cost; expected cycles per element
         return p;
     };
-    // Estimated cost of a configuration: sectors per element (1/4 is ideal on each side) from replaying the
-    // first tile of each class, weighted by the class's share of the elements, plus a small charge per warp
-    // instruction so that sparse tiles lose against full ones.
-    auto cost = [&](const AutPlan &p) {
-        double total = 0;
-        for (int c = 0; c < 2; ++c) {
-            const AutClass &C = p.cls[c];
-            const double share = (double)(C.j_end - C.j_begin) * C.gap / n;
-            if (share == 0) continue;
-            uint64_t sec = 0, el = 0, wi = 0;
-            autdetail::tile_cost(p, C.tile_begin, &sec, &el, &wi);
-            total += share * ((double)sec + 0.5 * (double)wi) / (double)el;
-        }
-        return total;
-    };
+    auto cost = [&](const AutPlan &) { return built_cost; };
     // Subtractive Euclid over (u, alpha), (v, beta).  Inside a run of equal steps the states change linearly,
     // so they are sampled geometrically (1, 2, 4, ... steps into the run, and its last two states).
     uint64_t u = 1, alpha = base.kmod, v = 1, beta = n - base.kmod;

@@ -612,6 +612,80 @@ size_t fuse_ops(std::vector<VecOp> &ops, const Loc *final_loc, const aloha *E) {
             break;
         }
     }
+    // Fast basis extension (hks.py: digits of several limbs, several special primes): per source limb
+    //   VCPY | VFQMOD  ->  VFQMUL.vs  ->  VFQADD.vv into a running sum   [ -> VFQSUB.vs ]
+    // with every intermediate a single-use, dead temporary.  The whole sum becomes one K_BEXT op that
+    // evaluates the same RTL functions in the same order.
+    {
+        auto intact = [&](size_t from, size_t to, const u64 *p, u64 len) {      // nobody in (from, to) writes [p, p+len)
+            for (size_t j = from + 1; j < to; ++j)
+                if (!ops[j].dead && overlap(ops[j].dst, ops[j].n, p, len)) return false;
+            return true;
+        };
+        auto same_mod = [&](const VecOp &x, const VecOp &y) { return x.q == y.q && x.iq == y.iq && x.n == y.n; };
+        // the summands op `m` stands for when consumed at `at` (m is a partial sum, or a VFQMUL.vs possibly fed
+        // by a VCPY / VFQMOD), and the ops that disappear if the caller fuses them
+        auto as_ext = [&](int m, size_t at, std::vector<ExtTerm> *out, std::vector<int> *kill) {
+            VecOp &mo = ops[m];
+            if (mo.dead || !single_use_temp(m)) return false;
+            if (mo.kind == K_BEXT && !mo.post) {
+                for (auto &t : mo.ext) if (!intact(m, at, t.x, mo.n)) return false;
+                *out = mo.ext;
+                kill->push_back(m);
+                return true;
+            }
+            if (mo.kind != K_EW || mo.alu != A_MULVS) return false;
+            const int pe = prod_a[m];
+            if (pe >= 0 && !ops[pe].dead && ops[pe].kind == K_EW && same_mod(ops[pe], mo) && single_use_temp(pe)) {
+                const VecOp &e = ops[pe];
+                const u32 pre = (e.alu == A_ADDVS && e.s == 0) ? (u32)PRE_VCPY : e.alu == A_MOD ? (u32)PRE_VFQMOD : 0u;
+                if (pre && intact(pe, at, e.a, e.n)) {
+                    out->push_back(ExtTerm{e.a, mo.s, pre});
+                    kill->push_back(pe);
+                    kill->push_back(m);
+                    return true;
+                }
+            }
+            if (!intact(m, at, mo.a, mo.n)) return false;
+            out->push_back(ExtTerm{mo.a, mo.s, 0});
+            kill->push_back(m);
+            return true;
+        };
+        for (size_t i = 0; i < n; ++i) {
+            VecOp &o = ops[i];
+            if (o.dead || o.kind != K_EW) continue;
+            if (o.alu == A_ADDVV) {
+                const int pa = prod_a[i], pb = prod_b[i];
+                if (pa < 0 || pb < 0 || pa == pb || !same_mod(ops[pa], o) || !same_mod(ops[pb], o)) continue;
+                std::vector<ExtTerm> ta, tb;
+                std::vector<int> kill;
+                if (!as_ext(pa, i, &ta, &kill) || !as_ext(pb, i, &tb, &kill) || ta.size() + tb.size() > 64) continue;
+                bool alias = false;             // the fused kernel reads every x while it writes dst
+                for (auto *v : {&ta, &tb}) for (auto &t : *v) if (t.x != o.dst && overlap(o.dst, o.n, t.x, o.n)) alias = true;
+                if (alias) continue;
+                for (int d : kill) { ops[d].dead = true; ++fused; }
+                ta.insert(ta.end(), tb.begin(), tb.end());
+                o.kind = K_BEXT;
+                o.ext = std::move(ta);
+                o.a = o.b = nullptr;
+                o.alu = 0;
+            } else if (o.alu == A_SUBVS) {
+                const int pa = prod_a[i];
+                if (pa < 0 || ops[pa].dead || ops[pa].kind != K_BEXT || ops[pa].post || !same_mod(ops[pa], o) || !single_use_temp(pa)) continue;
+                bool ok = true;
+                for (auto &t : ops[pa].ext) if (!intact(pa, i, t.x, o.n) || (t.x != o.dst && overlap(o.dst, o.n, t.x, o.n))) ok = false;
+                if (!ok) continue;
+                o.kind = K_BEXT;
+                o.ext = ops[pa].ext;
+                o.post = 1;
+                o.post_s = o.s;
+                o.a = nullptr;
+                o.alu = 0;
+                ops[pa].dead = true;
+                ++fused;
+            }
+        }
+    }
     // VCPY / VFQMOD feeding exactly one forward transform under the same modulus (the key-switch base
     // extension): the transform applies the op while loading, the intermediate never exists.
     for (size_t i = 0; i < n; ++i) {
@@ -727,9 +801,11 @@ void assign_levels(std::vector<VecOp> &ops, bool sequential) {
         int lvl = std::max(scan(o.a, o.n, false), scan(o.b, o.n, false));
         lvl = std::max(lvl, scan(o.c, o.n, false));
         for (auto &tm : o.terms) lvl = std::max(lvl, std::max(scan(tm.first, o.n, false), scan(tm.second, o.n, false)));
+        for (auto &tm : o.ext) lvl = std::max(lvl, scan(tm.x, o.n, false));
         lvl = std::max(lvl, scan(o.dst, o.n, true));
         o.level = lvl + 1;
         for (auto &tm : o.terms) { touch(tm.first, o.n, o.level, false); touch(tm.second, o.n, o.level, false); }
+        for (auto &tm : o.ext) touch(tm.x, o.n, o.level, false);
         touch(o.a, o.n, o.level, false);
         touch(o.b, o.n, o.level, false);
         touch(o.c, o.n, o.level, false);
@@ -791,7 +867,7 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
                 std::copy(grouped.begin(), grouped.end(), order.begin() + c);
                 std::copy(rest.begin(), rest.end(), order.begin() + c + grouped.size());
             }
-            std::vector<std::pair<size_t, const VecOp *>> sop_jobs;
+            std::vector<std::pair<size_t, const VecOp *>> sop_jobs, bext_jobs;
             for (size_t t = c; t < c + cnt; ++t) {
                 const VecOp &o = ops[order[t]];
                 switch (o.kind) {
@@ -809,6 +885,11 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
                 case K_SOP: {
                     const size_t at = append(tables, SopJob{o.dst, nullptr, o.q, o.iq, (u32)o.terms.size(), 0});
                     sop_jobs.emplace_back(at, &o);
+                    break;
+                }
+                case K_BEXT: {
+                    const size_t at = append(tables, BextJob{o.dst, nullptr, o.q, o.iq, o.post_s, (u32)o.ext.size(), o.post});
+                    bext_jobs.emplace_back(at, &o);
                     break;
                 }
                 case K_AUTMAC: {
@@ -859,6 +940,11 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
                 fixups.emplace_back(sj.first + offsetof(SopJob, pairs), tables.size());
                 for (auto &tm : sj.second->terms) { append(tables, tm.first); append(tables, tm.second); }
             }
+            for (auto &bj : bext_jobs) {
+                while (tables.size() % 16) tables.push_back(0);
+                fixups.emplace_back(bj.first + offsetof(BextJob, terms), tables.size());
+                for (auto &tm : bj.second->ext) append(tables, BextTerm{tm.x, tm.s, tm.pre});
+            }
             while (tables.size() % 16) tables.push_back(0);
             plan->launches.push_back(L);
             c += cnt;
@@ -902,9 +988,10 @@ int issue(aloha *E, const Plan &plan, u64 *launched) {
         case K_PEASE_I: e = launch_pease((const PeaseJob *)tab, L.njobs, ilog2(L.n), L.alu, true, E->stream); break;
         case K_MULADD: e = launch_muladd((const MulAddJob *)tab, L.njobs, L.n, E->stream); break;
         case K_SOP: e = launch_sop((const SopJob *)tab, L.njobs, L.n, E->stream); break;
+        case K_BEXT: e = launch_bext((const BextJob *)tab, L.njobs, L.n, E->stream); break;
         case K_AUTMAC:
-            e = (E->cfg.flags & ALOHA_F_AUT_GATHER) ? launch_autmac((const AutMacJob *)tab, L.njobs, L.n, E->stream)
-                                                    : launch_autmac_tiled((const AutMacJob *)tab, L.njobs, L.n, L.aux, E->stream);
+            e = (E->cfg.flags & ALOHA_F_AUT_TILED) ? launch_autmac_tiled((const AutMacJob *)tab, L.njobs, L.n, L.aux, E->stream)
+                                                   : launch_autmac((const AutMacJob *)tab, L.njobs, L.n, E->stream);
             break;
         case K_VAUT:
             e = (E->cfg.flags & ALOHA_F_AUT_GATHER) ? launch_vaut((const PermJob *)tab, L.njobs, L.n, E->stream)

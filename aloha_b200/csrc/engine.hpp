@@ -40,7 +40,9 @@ struct Loc {
     u64 n = 0;     // valid words
 };
 
-enum OpKind : uint8_t { K_EW = 0, K_NTT, K_INTT, K_VAUT, K_VROLI, K_COPY, K_MULADD, K_AUTMAC, K_SOP, K_PEASE_F, K_PEASE_I };
+enum OpKind : uint8_t { K_EW = 0, K_NTT, K_INTT, K_VAUT, K_VROLI, K_COPY, K_MULADD, K_AUTMAC, K_SOP, K_PEASE_F, K_PEASE_I, K_BEXT };
+
+struct ExtTerm { const u64 *x; u64 s; u32 pre; };   // one summand of a fused base extension (kernels.cuh BextTerm)
 
 struct VecOp {
     OpKind kind;
@@ -50,6 +52,9 @@ struct VecOp {
     const u64 *a = nullptr, *b = nullptr, *c = nullptr;   // c: addend of the fused forms
     bool dead = false;                                     // removed by the fusion pass
     std::vector<std::pair<const u64 *, const u64 *>> terms;   // K_SOP: dst = sum_t a_t * b_t (in this order)
+    std::vector<ExtTerm> ext;                              // K_BEXT: dst = sum_t pre_t(x_t) * s_t  [- post_s]
+    u64 post_s = 0;
+    u32 post = 0;
     u64 s = 0, q = 0, iq = 0, k = 0, kinv = 0;
     u32 pre = 0;                                           // K_NTT: base-extension op folded into the load
     int mod = -1;

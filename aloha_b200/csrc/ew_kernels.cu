@@ -264,6 +264,46 @@ __global__ void __launch_bounds__(kThreads) sop_kernel(const SopJob *__restrict_
     st2(job.dst + i, acc0, acc1);
 }
 
+// Fast basis extension: sum over source limbs of (x_t reduced into this modulus) * constant_t, evaluated with
+// the RTL's VCPY / VFQMOD, VFQMUL.vs and VFQADD.vv in instruction order, then an optional VFQSUB.vs.
+__global__ void __launch_bounds__(kThreads) bext_kernel(const BextJob *__restrict__ jobs, u32 n) {
+    const BextJob job = jobs[blockIdx.y];
+    const u64 q = job.q, iq = job.iq;
+    const u32 i = (blockIdx.x * kThreads + threadIdx.x) * kVec;
+    if (i >= n) return;
+    u64 acc0 = 0, acc1 = 0;
+    constexpr u32 kU = 4;                       // operands in flight per thread
+    auto term = [&](const BextTerm &tm, const ulonglong2 &v, bool first) {
+        u64 a0 = v.x, a1 = v.y;
+        if (tm.pre == PRE_VCPY) { a0 = rtl_alu<ALU_ADD_VS>(a0, 0, 0, q, iq); a1 = rtl_alu<ALU_ADD_VS>(a1, 0, 0, q, iq); }
+        else if (tm.pre == PRE_VFQMOD) { a0 = rtl_alu<ALU_MOD>(a0, 0, 0, q, iq); a1 = rtl_alu<ALU_MOD>(a1, 0, 0, q, iq); }
+        const u64 m0 = rtl_alu<ALU_MUL_VS>(a0, 0, tm.s, q, iq), m1 = rtl_alu<ALU_MUL_VS>(a1, 0, tm.s, q, iq);
+        if (first) { acc0 = m0; acc1 = m1; }
+        else { acc0 = rtl_alu<ALU_ADD_VV>(acc0, m0, 0, q, iq); acc1 = rtl_alu<ALU_ADD_VV>(acc1, m1, 0, q, iq); }
+    };
+    u32 t = 0;
+    for (; t + kU <= job.nterms; t += kU) {
+        BextTerm tm[kU];
+        ulonglong2 v[kU];
+#pragma unroll
+        for (u32 u = 0; u < kU; ++u) {
+            tm[u] = job.terms[t + u];
+            v[u] = ld2(tm[u].x + i);
+        }
+#pragma unroll
+        for (u32 u = 0; u < kU; ++u) term(tm[u], v[u], t + u == 0);
+    }
+    for (; t < job.nterms; ++t) {
+        const BextTerm tm = job.terms[t];
+        term(tm, ld2(tm.x + i), t == 0);
+    }
+    if (job.post == 1) {
+        acc0 = rtl_alu<ALU_SUB_VS>(acc0, 0, job.post_s, q, iq);
+        acc1 = rtl_alu<ALU_SUB_VS>(acc1, 0, job.post_s, q, iq);
+    }
+    st2(job.dst + i, acc0, acc1);
+}
+
 // ALOHA_F_STRICT transforms: one launch per stage of the RTL's constant-geometry schedule
 // (src/vp/ntt/ntt_fsm.sv:49-81; net effect per stage in SURVEY 3.3), every butterfly evaluated with the
 // RTL ALU's CT / GS opcodes (modalu.sv:160-165, 296-327) -- so the result, and the ping-pong
@@ -357,6 +397,11 @@ cudaError_t launch_mac(const MacJob *jobs, u32 njobs, u32 terms, u32 n, cudaStre
 }
 cudaError_t launch_sop(const SopJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
     sop_kernel<<<dim3((n / kVec + kThreads - 1) / kThreads, njobs), kThreads, 0, st>>>(jobs, n);
+    ++g_launches;
+    return cudaGetLastError();
+}
+cudaError_t launch_bext(const BextJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
+    bext_kernel<<<dim3((n / kVec + kThreads - 1) / kThreads, njobs), kThreads, 0, st>>>(jobs, n);
     ++g_launches;
     return cudaGetLastError();
 }

@@ -127,6 +127,23 @@ struct SopJob {
     u32 terms, pad;
 };
 
+// Fast basis extension (the key-switch's ModUp / ModDown inner loop, hks.py): per source limb a VCPY or VFQMOD
+// into the target modulus, a VFQMUL.vs by the limb's constant and a VFQADD into the running sum, optionally a
+// final VFQSUB.vs -- one pass over the operands instead of three per term.
+//   dst = [ (((m_0 + m_1) + m_2) + ...) - post_s ],   m_t = barrett(r(pre_t(x_t)), s_t)
+struct BextTerm {
+    const u64 *x;
+    u64 s;                 // scalar (already reduced once, as modalu.sv:46 does)
+    u64 pre;               // NttPre: 0 none, 1 VCPY, 2 VFQMOD
+};
+struct BextJob {
+    u64 *dst;
+    const BextTerm *terms;
+    u64 q, iq;
+    u64 post_s;            // VFQSUB.vs scalar (reduced once)
+    u32 nterms, post;      // post: 0 none, 1 subtract post_s
+};
+
 // dst = c + aut_k(x) * p   (rotate-and-sum inner step: VAUT, VFQMUL.vv, VFQADD.vv fused)
 struct AutMacJob {
     u64 *dst;
@@ -190,6 +207,7 @@ cudaError_t launch_mac(const MacJob *jobs_dev, u32 njobs, u32 terms, u32 n, cuda
 cudaError_t launch_autmac(const AutMacJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
 cudaError_t launch_sop(const SopJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
 cudaError_t launch_muladd(const MulAddJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
+cudaError_t launch_bext(const BextJob *jobs_dev, u32 njobs, u32 n, cudaStream_t st);
 
 // number of kernel launches issued by the launchers above since process start (bench accounting)
 unsigned long long kernel_launch_count();

@@ -219,6 +219,9 @@ def run_gpu(args):
                                     shapes=args.shapes.split(",") if args.shapes else None)
         elif args.only == "tv":
             out = measure_tv_latency(A) if rank == 0 else None
+        elif args.only == "rotmac_tiled":
+            out = measure_rotmac(torch, A, asm, {"device": local}, primes, psis, stream, timed0, args.polys, flags=A.F_AUT_TILED,
+                                 quick=args.quick, only_k=args.galois)
         elif args.only == "rotmac_gather":
             out = measure_rotmac(torch, A, asm, {"device": local}, primes, psis, stream, timed0, args.polys, flags=A.F_AUT_GATHER,
                                  quick=args.quick, only_k=args.galois)
@@ -571,8 +574,11 @@ def measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, polys
                                "launches_per_step": (s1["kernel_launches"] - s0["kernel_launches"]) / steps,
                                "checked_against_oracle": good}
     eng.close()
-    out = {"polys": polys, "limbs": LIMBS, "n": N, "kernel": "gather (ALOHA_F_AUT_GATHER)" if flags & A.F_AUT_GATHER else
-           "shared-memory tile permutation (aut_plan.hpp)", "all_checked_against_oracle": ok}
+    out = {"polys": polys, "limbs": LIMBS, "n": N,
+           "kernels": "8-byte gather for both (ALOHA_F_AUT_GATHER)" if flags & A.F_AUT_GATHER else
+                      "shared-memory tile permutation for both (ALOHA_F_AUT_TILED)" if flags & A.F_AUT_TILED else
+                      "vaut: shared-memory tile permutation (aut_plan.hpp); rotate_mac: fused gather-multiply-add",
+           "all_checked_against_oracle": ok}
     for kind, bytes_per, unit in (("vaut", 2 * N * 8, "limb automorphisms/s"), ("rotate_mac", 4 * N * 8, "limb rotate-MACs/s")):
         vals = [v["value"] for v in res[kind].values()]
         worst = min(vals)
@@ -729,7 +735,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the rotate-MAC and key-switch workloads")
     ap.add_argument("--shapes", default="", help="with --only keyswitch: comma-separated names from KS_SHAPES")
     ap.add_argument("--galois", default="", help="with --only rotmac: one Galois element by name, e.g. 3^18")
-    ap.add_argument("--only", default="", choices=["", "keyswitch", "rotmac", "rotmac_gather", "tv"], help="profiling: run one extra workload alone")
+    ap.add_argument("--only", default="", choices=["", "keyswitch", "rotmac", "rotmac_gather", "rotmac_tiled", "tv"], help="profiling: run one extra workload alone")
     args = ap.parse_args()
     globals()["POLYS"] = args.polys
     if args.impl == "reference":

@@ -78,9 +78,12 @@ enum {
     ALOHA_F_STRICT = 1u << 4,    /* VNTT / VINTT run the RTL's constant-geometry schedule stage by stage with the
                                     RTL ALU: word-exact for ANY input (also >= 2q) and the source register keeps the
                                     ping-pong intermediate the RTL leaves there.  ~10x slower transforms. */
-    ALOHA_F_AUT_GATHER = 1u << 7,  /* VAUT (and the fused rotate-MAC) as a destination-ordered 8-byte gather from L2 instead
-                                    of the shared-memory tile permutation that moves both sides in whole lines.  Same
-                                    results; for A/B measurements and tests. */
+    ALOHA_F_AUT_GATHER = 1u << 7,  /* Automorphisms have two kernels: a shared-memory tile permutation that moves both sides
+                                    in whole lines (aut_plan.hpp) and a destination-ordered 8-byte gather from L2.  By
+                                    default a standalone VAUT takes the tiles (the gather is bound by L2 transactions, one
+                                    per element) and the fused rotate-MAC takes the gather (one stream in four: the
+                                    transactions hide behind the other three).  This flag forces the gather for both, */
+    ALOHA_F_AUT_TILED = 1u << 8,   /* this one the tiles for both.  Same results; for A/B measurements and tests. */
     ALOHA_F_GENERIC_MODMUL = 1u << 6  /* transforms use the any-prime (Shoup) arithmetic even for moduli of the form
                                     2^60 - d, d <= 2^27, which otherwise take the cheaper pseudo-Mersenne product.
                                     Same results; for A/B measurements and tests. */

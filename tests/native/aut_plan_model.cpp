@@ -17,9 +17,9 @@ typedef unsigned long long u64;
 extern "C" {
 
 // out: mask, kmod, kinv, ntiles, then per class: j_begin, j_end, gap, log_jb, log_fb, fblocks, stride, tile_begin
-int aut_model_plan(uint32_t n, u64 k, uint32_t out[20]) {
+int aut_model_plan(uint32_t n, u64 k, uint32_t out[22]) {
     const AutPlan p = make_aut_plan(n, k);
-    static_assert(sizeof(AutPlan) == 20 * sizeof(uint32_t), "flat layout");
+    static_assert(sizeof(AutPlan) == 22 * sizeof(uint32_t), "flat layout");
     std::memcpy(out, &p, sizeof p);
     return 0;
 }
@@ -42,10 +42,10 @@ int aut_model_apply(uint32_t n, u64 k, u64 q, const u64 *src, u64 *dst, u64 stat
         // each thread walking its 8 slots exactly as the kernel does (incremental indices).
         struct Access { bool valid; uint32_t i, d, sm; };
         for (int phase = 0; phase < 2; ++phase) {
-            std::vector<std::vector<Access>> acc(kAutThreads, std::vector<Access>(8));
+            std::vector<std::vector<Access>> acc(kAutThreads, std::vector<Access>(kAutTile / kAutThreads));
             for (uint32_t tid = 0; tid < kAutThreads; ++tid) {
                 auto walk = [&](auto w) {
-                    for (int it = 0; it < 8; ++it) {
+                    for (int it = 0; it < (int)(kAutTile / kAutThreads); ++it) {
                         Access a{!w.idle() && w.valid(), w.i, 0, w.sm};
                         if constexpr (std::is_same_v<decltype(w), AutStoreWalk<true>> || std::is_same_v<decltype(w), AutStoreWalk<false>>) a.d = w.d;
                         acc[tid][it] = a;
@@ -55,7 +55,7 @@ int aut_model_apply(uint32_t n, u64 k, u64 q, const u64 *src, u64 *dst, u64 stat
                 if (phase == 0) { if (T.log_jb > 8) walk(AutLoadWalk<true>(P, T, tid)); else walk(AutLoadWalk<false>(P, T, tid)); }
                 else { if (T.log_fb > 8) walk(AutStoreWalk<true>(P, T, tid)); else walk(AutStoreWalk<false>(P, T, tid)); }
             }
-            for (int it = 0; it < 8; ++it)
+            for (int it = 0; it < (int)(kAutTile / kAutThreads); ++it)
                 for (uint32_t warp = 0; warp < 8; ++warp) {
                     std::set<uint32_t> sectors;
                     uint32_t bank[2][16] = {};

@@ -17,7 +17,7 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 FLAG_SETS = [0, A.F_NO_BATCH, A.F_NO_ALIAS, A.F_NO_BATCH | A.F_NO_ALIAS, A.F_GRAPHS, A.F_NO_FUSE, A.F_STRICT, A.F_DEFER,
-             A.F_AUT_GATHER]
+             A.F_AUT_GATHER, A.F_AUT_TILED]
 
 
 def tv_engine(flags=0):
@@ -313,7 +313,7 @@ def test_rotate_mac_stream_vs_oracle():
     assert eng.stats()["ops_fused"] == 2 * (L - 1)
 
 
-@pytest.mark.parametrize("flags", [0, A.F_AUT_GATHER])
+@pytest.mark.parametrize("flags", [0, A.F_AUT_GATHER, A.F_AUT_TILED])
 @pytest.mark.parametrize("n", [256, 2048, 65536])
 def test_vaut_every_kind_of_galois_element(n, flags):
     """The tiled permutation (aut_plan.hpp) and the 8-byte gather against the oracle for Galois elements
@@ -335,7 +335,7 @@ def test_vaut_every_kind_of_galois_element(n, flags):
     assert eng.stats()["kernel_launches"] == 1
 
 
-@pytest.mark.parametrize("flags", [0, A.F_AUT_GATHER])
+@pytest.mark.parametrize("flags", [0, A.F_AUT_GATHER, A.F_AUT_TILED])
 def test_rotate_mac_full_size_vs_oracle(flags):
     """BASELINE.json configs[3] at its real size: N = 2^16, 32 limbs, fused aut-mul-add, every word of two
     polynomials' worth of limbs against the oracle, for a small, a pseudo-random and a >= N Galois element."""
@@ -381,7 +381,7 @@ def test_fusion_keeps_in_place_rotate_accumulate_exact():
     pa = rng.integers(0, q, (2, n), dtype=np.uint64)
     k = pow(3, 5, 2 * n)
     outs = []
-    for flags in (0, A.F_NO_FUSE | A.F_NO_BATCH, A.F_AUT_GATHER):
+    for flags in (0, A.F_NO_FUSE | A.F_NO_BATCH, A.F_AUT_GATHER, A.F_AUT_TILED):
         eng = A.Engine(vlmax_bits=n * 64, spm_rows=(calls + 2) * rp, ksk_rows=0, moduli=(), flags=flags, pool_buffers=34)
         eng.load_isram(prog.words(), 0)
         eng.dma_mem_h2d(0, m0.reshape(-1))
