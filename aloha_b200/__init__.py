@@ -384,6 +384,9 @@ class HostDriver:
         if getattr(self, "h", None):
             self.L.aloha_host_destroy(self.h)
             self.h = None
+            for p in getattr(self, "_pinned_blocks", []):
+                self.L.aloha_pinned_free(p)
+            self._pinned_blocks, self._dump_pool = [], []
 
     __del__ = close
 
@@ -430,15 +433,28 @@ class HostDriver:
         out.append((None, dump, wr.astype(bool)))
         return out
 
+    def _pinned(self, nwords: int) -> np.ndarray:
+        """a page-locked uint64 array owned by this driver (freed in close())"""
+        p = C.c_void_p()
+        rc = self.L.aloha_pinned_alloc(nwords * 8, C.byref(p))
+        if rc:
+            raise AlohaError(rc, "pinned_alloc")
+        self._pinned_blocks.append(p)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(nwords,))
+
     def run_all_async(self, first: int = 0, count: int | None = None):
         """Ops [first, first+count) with every dump the testbench would write, read-backs overlapped with the
-        following ops, one synchronisation at the end.  -> per op, the same list run_op returns."""
+        following ops, one synchronisation at the end.  -> per op, the same list run_op returns.  The dump
+        arrays are page-locked, owned by this driver and reused by the next call."""
         count = len(self) - first if count is None else count
         w = 4 * self.n
+        if not hasattr(self, "_pinned_blocks"):
+            self._pinned_blocks, self._dump_pool = [], []
+        while len(self._dump_pool) < count:
+            self._dump_pool.append((self._pinned(w), self._pinned(w), np.empty(w, np.uint8), np.empty(w, np.uint8)))
         res = []
-        for i in range(first, first + count):
-            dump, sub = np.empty(w, np.uint64), np.empty(w, np.uint64)
-            wr, swr = np.empty(w, np.uint8), np.empty(w, np.uint8)
+        for n_, i in enumerate(range(first, first + count)):
+            dump, sub, wr, swr = self._dump_pool[n_]
             has_sub = C.c_int(0)
             rc = self.L.aloha_host_run_op_async(self.h, i, _p64(dump), _p8(wr), _p64(sub), _p8(swr), C.byref(has_sub))
             if rc:

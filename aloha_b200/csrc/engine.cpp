@@ -888,7 +888,12 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
                     break;
                 }
                 case K_BEXT: {
-                    const size_t at = append(tables, BextJob{o.dst, nullptr, o.q, o.iq, o.post_s, (u32)o.ext.size(), o.post});
+                    // the lazy path needs q to be a 60-bit modulus with its own Barrett constant and canonical scalars
+                    bool fast = o.q > (1ull << 59) && o.q < (1ull << 60) && o.iq == (u64)((((u128)1) << 121) / o.q) &&
+                                (!o.post || o.post_s < o.q);
+                    for (auto &tm : o.ext) fast = fast && tm.s < o.q;
+                    const u32 mest = fast ? (u32)((((u128)1) << 91) / o.q) : 0u;
+                    const size_t at = append(tables, BextJob{o.dst, nullptr, o.q, o.iq, o.post_s, (u32)o.ext.size(), o.post, fast ? 1u : 0u, mest});
                     bext_jobs.emplace_back(at, &o);
                     break;
                 }
@@ -943,7 +948,8 @@ int compile_plan(aloha *E, Builder &B, Plan *plan) {
             for (auto &bj : bext_jobs) {
                 while (tables.size() % 16) tables.push_back(0);
                 fixups.emplace_back(bj.first + offsetof(BextJob, terms), tables.size());
-                for (auto &tm : bj.second->ext) append(tables, BextTerm{tm.x, tm.s, tm.pre});
+                for (auto &tm : bj.second->ext)
+                    append(tables, BextTerm{tm.x, tm.s, tm.s < bj.second->q ? (u64)(((u128)tm.s << 64) / bj.second->q) : 0ull, tm.pre});
             }
             while (tables.size() % 16) tables.push_back(0);
             plan->launches.push_back(L);

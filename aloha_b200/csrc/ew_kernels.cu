@@ -264,22 +264,54 @@ __global__ void __launch_bounds__(kThreads) sop_kernel(const SopJob *__restrict_
     st2(job.dst + i, acc0, acc1);
 }
 
-// Fast basis extension: sum over source limbs of (x_t reduced into this modulus) * constant_t, evaluated with
-// the RTL's VCPY / VFQMOD, VFQMUL.vs and VFQADD.vv in instruction order, then an optional VFQSUB.vs.
+// Fast basis extension: sum over source limbs of (x_t reduced into this modulus) * constant_t, then an
+// optional VFQSUB.vs.  Reference semantics = the RTL's VCPY / VFQMOD, VFQMUL.vs and VFQADD.vv in instruction
+// order (bext_rtl below, word for word).
+//
+// When iq is q's Barrett constant and every operand reaching a multiply is canonical, rtl_barrett(a, s) is
+// exactly a * s mod q and the chain of RTL adds is exactly the modular sum, so ANY exact evaluation stores the
+// same words.  The fast path uses one: lazy Shoup products (in [0, 2q), for any 64-bit operand) summed
+// without reduction, one canonical reduction at the end.  An input word is in the fast domain when the RTL's
+// own conditional subtracts would have made it canonical: x < 4q behind a VCPY (two subtracts there, one in
+// the multiply), any word behind a VFQMOD, x < 2q with no pre-op.  Anything else (never produced by the
+// generated streams) takes the RTL chain for that element.
+__device__ __forceinline__ u64 bext_rtl(const BextJob &job, u32 i, u32 lane_word) {
+    const u64 q = job.q, iq = job.iq;
+    u64 acc = 0;
+    for (u32 t = 0; t < job.nterms; ++t) {
+        const BextTerm tm = job.terms[t];
+        u64 a = tm.x[i + lane_word];
+        if (tm.pre == PRE_VCPY) a = rtl_alu<ALU_ADD_VS>(a, 0, 0, q, iq);
+        else if (tm.pre == PRE_VFQMOD) a = rtl_alu<ALU_MOD>(a, 0, 0, q, iq);
+        const u64 m = rtl_alu<ALU_MUL_VS>(a, 0, tm.s, q, iq);
+        acc = t == 0 ? m : rtl_alu<ALU_ADD_VV>(acc, m, 0, q, iq);
+    }
+    if (job.post == 1) acc = rtl_alu<ALU_SUB_VS>(acc, 0, job.post_s, q, iq);
+    return acc;
+}
+
 __global__ void __launch_bounds__(kThreads) bext_kernel(const BextJob *__restrict__ jobs, u32 n) {
     const BextJob job = jobs[blockIdx.y];
-    const u64 q = job.q, iq = job.iq;
+    const u64 q = job.q;
     const u32 i = (blockIdx.x * kThreads + threadIdx.x) * kVec;
     if (i >= n) return;
+    if (!job.fast) {
+        st2(job.dst + i, bext_rtl(job, i, 0), bext_rtl(job, i, 1));
+        return;
+    }
+    const u64 nq = 0 - q, q2 = 2 * q, q4 = 4 * q;
     u64 acc0 = 0, acc1 = 0;
+    bool out_of_domain = false;
     constexpr u32 kU = 4;                       // operands in flight per thread
-    auto term = [&](const BextTerm &tm, const ulonglong2 &v, bool first) {
+    auto term = [&](const BextTerm &tm, const ulonglong2 &v, u32 count) {
         u64 a0 = v.x, a1 = v.y;
-        if (tm.pre == PRE_VCPY) { a0 = rtl_alu<ALU_ADD_VS>(a0, 0, 0, q, iq); a1 = rtl_alu<ALU_ADD_VS>(a1, 0, 0, q, iq); }
-        else if (tm.pre == PRE_VFQMOD) { a0 = rtl_alu<ALU_MOD>(a0, 0, 0, q, iq); a1 = rtl_alu<ALU_MOD>(a1, 0, 0, q, iq); }
-        const u64 m0 = rtl_alu<ALU_MUL_VS>(a0, 0, tm.s, q, iq), m1 = rtl_alu<ALU_MUL_VS>(a1, 0, tm.s, q, iq);
-        if (first) { acc0 = m0; acc1 = m1; }
-        else { acc0 = rtl_alu<ALU_ADD_VV>(acc0, m0, 0, q, iq); acc1 = rtl_alu<ALU_ADD_VV>(acc1, m1, 0, q, iq); }
+        // VFQMOD is x mod q for every word, and the Shoup product below takes any 64-bit word: nothing to do for it
+        if (tm.pre == PRE_VCPY) out_of_domain |= (a0 >= q4) | (a1 >= q4);
+        else if (tm.pre != PRE_VFQMOD) out_of_domain |= (a0 >= q2) | (a1 >= q2);
+        // every 7 lazy products (each below 2q) the running sums (then below 16q) are brought back below 2q
+        if (count && count % 7 == 0) { acc0 = csub_s(csub_s(csub_s(acc0, 8 * q), q4), q2); acc1 = csub_s(csub_s(csub_s(acc1, 8 * q), q4), q2); }
+        acc0 = shoup_mac(acc0, a0, tm.s, tm.sp, nq);
+        acc1 = shoup_mac(acc1, a1, tm.s, tm.sp, nq);
     };
     u32 t = 0;
     for (; t + kU <= job.nterms; t += kU) {
@@ -291,16 +323,20 @@ __global__ void __launch_bounds__(kThreads) bext_kernel(const BextJob *__restric
             v[u] = ld2(tm[u].x + i);
         }
 #pragma unroll
-        for (u32 u = 0; u < kU; ++u) term(tm[u], v[u], t + u == 0);
+        for (u32 u = 0; u < kU; ++u) term(tm[u], v[u], t + u);
     }
     for (; t < job.nterms; ++t) {
         const BextTerm tm = job.terms[t];
-        term(tm, ld2(tm.x + i), t == 0);
+        term(tm, ld2(tm.x + i), t);
     }
-    if (job.post == 1) {
-        acc0 = rtl_alu<ALU_SUB_VS>(acc0, 0, job.post_s, q, iq);
-        acc1 = rtl_alu<ALU_SUB_VS>(acc1, 0, job.post_s, q, iq);
+    if (out_of_domain) {                        // not taken by generated streams: RTL chain for these two words
+        st2(job.dst + i, bext_rtl(job, i, 0), bext_rtl(job, i, 1));
+        return;
     }
+    // below 16q -> canonical
+    acc0 = csub_s(csub_s(csub_s(csub_s(acc0, 8 * q), q4), q2), q);
+    acc1 = csub_s(csub_s(csub_s(csub_s(acc1, 8 * q), q4), q2), q);
+    if (job.post == 1) { acc0 = rtl_sub(acc0, job.post_s, q); acc1 = rtl_sub(acc1, job.post_s, q); }
     st2(job.dst + i, acc0, acc1);
 }
 

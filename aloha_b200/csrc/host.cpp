@@ -38,24 +38,27 @@ uint64_t pow3_mod(uint32_t e, uint64_t m) {
 
 }  // namespace
 
-// A dump (or a store to the modelled DDR) whose read-back is still in flight: the data lands in a slot of the
-// page-locked ring and is handed to its destination(s) by aloha_host_sync.
-struct PendingDump {
-    uint64_t slot;            // byte offset inside the ring
-    uint64_t bytes;
-    uint64_t *dump;           // caller's buffer (may be null for a plain store)
-    int64_t dram_addr;        // >= 0: also goes to the modelled DDR (store_cipher)
+// A store to the modelled DDR whose read-back is still in flight (the download channel writes straight into
+// the page-locked DDR image); its dump, if one was asked for, is copied out of the DDR by aloha_host_sync.
+struct PendingStore {
+    uint64_t dram_addr, bytes;
+    uint64_t *dump;           // caller's buffer, or null
 };
 
 struct aloha_host {
     aloha_t *eng;
     uint32_t n;
     std::vector<HostOp> ops;
-    std::vector<uint8_t> dram;
+    uint8_t *dram_data = nullptr;     // the modelled DDR, page-locked so both DMA channels reach it asynchronously
+    uint64_t dram_size = 0;
     std::map<uint32_t, std::vector<uint64_t>> encoder;
-    uint8_t *ring = nullptr;  // page-locked staging for asynchronous read-backs
-    uint64_t ring_bytes = 0, ring_used = 0;
-    std::vector<PendingDump> pending;
+    std::vector<PendingStore> pending;
+    bool in_flight = false;           // asynchronous read-backs issued since the last sync
+    struct Dram {                     // vector-like view used by the op code below
+        aloha_host *h;
+        uint8_t *data() const { return h->dram_data; }
+        uint64_t size() const { return h->dram_size; }
+    } dram{this};
 };
 
 extern "C" {
@@ -82,42 +85,45 @@ int aloha_host_create(aloha_t *eng, const char *program, uint64_t dram_bytes, ui
         }
         H->ops.push_back(op);
     }
-    H->dram.assign(dram_bytes, 0);
+    if (aloha_pinned_alloc(dram_bytes, (void **)&H->dram_data) != ALOHA_OK) { delete H; return ALOHA_E_NOMEM; }
+    std::memset(H->dram_data, 0, dram_bytes);
+    H->dram_size = dram_bytes;
     *out = H;
     return ALOHA_OK;
 }
 
 void aloha_host_destroy(aloha_host_t *H) {
     if (!H) return;
-    if (!H->pending.empty()) aloha_sync(H->eng);
-    aloha_pinned_free(H->ring);
+    if (H->in_flight) aloha_sync(H->eng);
+    aloha_pinned_free(H->dram_data);
     delete H;
 }
+
+int aloha_host_num_ops(const aloha_host_t *H) { return H ? (int)H->ops.size() : ALOHA_E_ARG; }
 
 // Every read-back requested through aloha_host_run_op_async so far is in its destination.
 int aloha_host_sync(aloha_host_t *H) {
     if (!H) return ALOHA_E_ARG;
     int rc = aloha_sync(H->eng);
     if (rc) return rc;
-    for (const PendingDump &p : H->pending) {
-        if (p.dram_addr >= 0) std::memcpy(H->dram.data() + p.dram_addr, H->ring + p.slot, p.bytes);
-        if (p.dump) std::memcpy(p.dump, H->ring + p.slot, p.bytes);
-    }
+    for (const PendingStore &p : H->pending)
+        if (p.dump) std::memcpy(p.dump, H->dram_data + p.dram_addr, p.bytes);
     H->pending.clear();
-    H->ring_used = 0;
+    H->in_flight = false;
     return ALOHA_OK;
 }
-int aloha_host_num_ops(const aloha_host_t *H) { return H ? (int)H->ops.size() : ALOHA_E_ARG; }
 
 int aloha_host_dram_write(aloha_host_t *H, uint64_t addr, const void *src, uint64_t bytes) {
     if (!H || !src) return ALOHA_E_ARG;
     if (addr + bytes > H->dram.size()) return ALOHA_E_RANGE;
+    if (H->in_flight) { int rc = aloha_host_sync(H); if (rc) return rc; }
     std::memcpy(H->dram.data() + addr, src, bytes);
     return ALOHA_OK;
 }
 int aloha_host_dram_read(aloha_host_t *H, uint64_t addr, void *dst, uint64_t bytes) {
     if (!H || !dst) return ALOHA_E_ARG;
     if (addr + bytes > H->dram.size()) return ALOHA_E_RANGE;
+    if (H->in_flight) { int rc = aloha_host_sync(H); if (rc) return rc; }
     std::memcpy(dst, H->dram.data() + addr, bytes);
     return ALOHA_OK;
 }
@@ -129,39 +135,18 @@ int aloha_host_set_encoder_output(aloha_host_t *H, uint32_t op_index, const uint
 
 namespace {
 
-// a ring slot for `bytes`, draining the ring first when it is full
-int ring_slot(aloha_host *H, uint64_t bytes, uint64_t *slot) {
-    if (!H->ring) {
-        H->ring_bytes = 64 * bytes;                       // 64 dumps in flight (16 MiB at N = 8192)
-        int rc = aloha_pinned_alloc(H->ring_bytes, (void **)&H->ring);
-        if (rc) return rc;
-    }
-    if (bytes > H->ring_bytes) return ALOHA_E_ARG;
-    if (H->ring_used + bytes > H->ring_bytes) {
-        int rc = aloha_host_sync(H);
-        if (rc) return rc;
-    }
-    *slot = H->ring_used;
-    H->ring_used += bytes;
-    return ALOHA_OK;
-}
-
-// SPM rows -> ring (asynchronous) -> `dump` and/or the modelled DDR at aloha_host_sync
-int read_back_async(aloha_host *H, uint32_t row, uint64_t bytes, uint64_t *dump, int64_t dram_addr) {
-    uint64_t slot;
-    int rc = ring_slot(H, bytes, &slot);
-    if (rc) return rc;
-    rc = aloha_dma_mem_d2h_async(H->eng, (uint64_t *)(H->ring + slot), row, bytes);
-    if (rc) return rc;
-    H->pending.push_back(PendingDump{slot, bytes, dump, dram_addr});
-    return ALOHA_OK;
+// SPM rows -> host buffer on the download channel; the buffer is valid after aloha_host_sync
+int read_back_async(aloha_host *H, uint32_t row, uint64_t bytes, uint64_t *dst) {
+    H->in_flight = true;
+    return aloha_dma_mem_d2h_async(H->eng, dst, row, bytes);
 }
 
 }  // namespace
 
 // aloha_host_run_op without the blocking read-backs: the op is issued, its dump(s) are copied out by the
 // engine's download channel while later ops run, and the caller's buffers are valid after aloha_host_sync.
-// The `written` masks are host-side state and are filled in immediately.
+// dump / sub_dump should be page-locked (aloha_pinned_alloc) -- pageable buffers work but make the copy
+// synchronous.  The `written` masks are host-side state and are filled in immediately.
 int aloha_host_run_op_async(aloha_host_t *H, uint32_t i, uint64_t *dump, uint8_t *written, uint64_t *sub_dump,
                             uint8_t *sub_written, int *has_sub) {
     if (!H || i >= H->ops.size()) return ALOHA_E_ARG;
@@ -175,21 +160,23 @@ int aloha_host_run_op_async(aloha_host_t *H, uint32_t i, uint64_t *dump, uint8_t
     case OP_LOAD: {
         const uint64_t a = kDramVpBase + op.dram_addr;
         if (a + bytes > H->dram.size()) return ALOHA_E_RANGE;
-        for (const PendingDump &p : H->pending)          // a store to these DDR bytes may still be in flight
-            if (p.dram_addr >= 0 && (uint64_t)p.dram_addr < a + bytes && a < (uint64_t)p.dram_addr + p.bytes) {
+        for (const PendingStore &p : H->pending)         // a store to these DDR bytes may still be in flight
+            if (p.dram_addr < a + bytes && a < p.dram_addr + p.bytes) {
                 rc = aloha_host_sync(H);
                 if (rc) return rc;
                 break;
             }
-        rc = aloha_dma_mem_h2d(E, op.spm_addr, (const uint64_t *)(H->dram.data() + a), bytes);
+        H->in_flight = true;                             // the upload channel reads the DDR image asynchronously
+        rc = aloha_dma_mem_h2d_async(E, op.spm_addr, (const uint64_t *)(H->dram.data() + a), bytes);
         break;
     }
     case OP_STORE: {
         const uint64_t a = kDramVpBase + op.dram_addr;
         if (a + bytes > H->dram.size()) return ALOHA_E_RANGE;
-        rc = read_back_async(H, op.spm_addr, bytes, want_dump ? dump : nullptr, (int64_t)a);
-        if (rc || !want_dump) return rc;
-        return aloha_spm_written(E, op.spm_addr, words, written);
+        rc = read_back_async(H, op.spm_addr, bytes, (uint64_t *)(H->dram.data() + a));
+        if (rc) return rc;
+        H->pending.push_back(PendingStore{a, bytes, want_dump ? dump : nullptr});
+        return want_dump ? aloha_spm_written(E, op.spm_addr, words, written) : ALOHA_OK;
     }
     case OP_ENCODE: {
         auto it = H->encoder.find(i);
@@ -197,7 +184,7 @@ int aloha_host_run_op_async(aloha_host_t *H, uint32_t i, uint64_t *dump, uint8_t
         rc = aloha_dma_mem_h2d(E, op.spm_addr, it->second.data(), it->second.size() * 8);
         if (rc) return rc;
         if (sub_dump && sub_written) {
-            rc = read_back_async(H, op.spm_addr, bytes, sub_dump, -1);
+            rc = read_back_async(H, op.spm_addr, bytes, sub_dump);
             if (!rc) rc = aloha_spm_written(E, op.spm_addr, words, sub_written);
             if (rc) return rc;
             if (has_sub) *has_sub = 1;
@@ -216,7 +203,7 @@ int aloha_host_run_op_async(aloha_host_t *H, uint32_t i, uint64_t *dump, uint8_t
     default: return ALOHA_E_OPCODE;
     }
     if (rc || !want_dump) return rc;
-    rc = read_back_async(H, op.spm_addr, bytes, dump, -1);
+    rc = read_back_async(H, op.spm_addr, bytes, dump);
     if (rc) return rc;
     // the mask describes SPM after this op: the run_vp above has been planned by now (aloha_spm_written
     // flushes a deferred queue), so the host-side bitmap is current
@@ -226,7 +213,7 @@ int aloha_host_run_op_async(aloha_host_t *H, uint32_t i, uint64_t *dump, uint8_t
 int aloha_host_run_op(aloha_host_t *H, uint32_t i, uint64_t *dump, uint8_t *written, uint64_t *sub_dump,
                       uint8_t *sub_written, int *has_sub) {
     if (!H || i >= H->ops.size()) return ALOHA_E_ARG;
-    if (!H->pending.empty()) {                            // mixing with the asynchronous flavour: drain first
+    if (H->in_flight) {                                   // mixing with the asynchronous flavour: drain first
         int rc0 = aloha_host_sync(H);
         if (rc0) return rc0;
     }

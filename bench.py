@@ -98,8 +98,15 @@ class ClockSampler:
         except Exception:
             pass
         if len(self.indices) > 1:
-            out["sm_mhz_min_per_gpu"] = {g: min(int(r[1]) for r in rows if r[0] == str(g)) for g in self.indices
-                                         if any(r[0] == str(g) for r in rows)}
+            per = {}
+            for g in self.indices:
+                mine = [r for r in rows if r[0] == str(g)]
+                if not mine:
+                    continue
+                pw = [float(r[7]) for r in mine if len(r) > 7]
+                per[g] = {"sm_mhz_median": int(np.median([int(r[1]) for r in mine])), "sm_mhz_min": min(int(r[1]) for r in mine),
+                          "power_w_max": max(pw) if pw else None, "power_w_median": float(np.median(pw)) if pw else None}
+            out["per_gpu"] = per
         return out
 
 
@@ -162,7 +169,7 @@ def run_reference(args):
         "impl": "reference", "metric": "limb_ntts_per_s_n65536", "value": value, "unit": "limb-NTTs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(),
+        "config": dict(workload_config(), reference_arm_sample=sample + " (a bounded sample of the 2048-limb-NTT step: the rate is what is compared)"),
         "cpu_baseline": {"value": value, "unit": "limb-NTTs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "limb-NTTs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -234,7 +241,7 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
     eng = A.Engine(vlmax_bits=N * 64, spm_rows=2 * rows, ksk_rows=0, device=local, moduli=list(zip(primes, psis)),
-                   l2_chunk_bytes=args.chunk_mib << 20)
+                   l2_chunk_bytes=args.chunk_mib << 20, flags=(A.F_GRAPHS if args.graphs else 0) | (A.F_GENERIC_MODMUL if args.generic else 0))
     # A dedicated non-default torch stream: the engine launches on it (aloha_set_stream) and the CUDA
     # events below are recorded on it.  (Stream handle 0 would mean "the engine's own stream".)
     stream = torch.cuda.Stream()
@@ -331,6 +338,37 @@ def run_gpu(args):
     ms_inv = timed(lambda: eng.run_vp_batch(1024, back), args.steps)
     inv_value = world * ntts_per_step * args.steps / (ms_inv / 1e3)
 
+    # the same workload with the any-prime (Shoup) arithmetic every kernel also carries -- what moduli that are
+    # not of the form 2^60 - d (the reference's own q0, q1, P) get
+    generic = None
+    if world == 1 and not args.generic:
+        eng.close()
+        eng = A.Engine(vlmax_bits=N * 64, spm_rows=2 * rows, ksk_rows=0, device=local, moduli=list(zip(primes, psis)),
+                       flags=A.F_GENERIC_MODMUL)
+        eng.set_stream(stream.cuda_stream)
+        eng.load_isram(asm.transform_stream(N, primes).words(), 0)
+        eng.load_isram(asm.transform_stream(N, primes, inverse=True).words(), 1024)
+        eng.dma_mem_h2d(0, (host_in.data_ptr(), nbytes))
+        for _ in range(5):
+            eng.run_vp_batch(0, calls)
+        ms_g = timed(lambda: eng.run_vp_batch(0, calls), args.steps)
+        for _ in range(3):
+            eng.run_vp_batch(1024, back)
+        ms_gi = timed(lambda: eng.run_vp_batch(1024, back), args.steps)
+        generic = {"value": ntts_per_step * args.steps / (ms_g / 1e3), "unit": "limb-NTTs/s", "ms_per_step": ms_g / args.steps,
+                   "intt": ntts_per_step * args.steps / (ms_gi / 1e3),
+                   "frac_of_hbm_peak": ntts_per_step * args.steps / (ms_g / 1e3) * ALG_BYTES_PER_NTT / 1e9 / peaks()[0],
+                   "note": "same primes, ALOHA_F_GENERIC_MODMUL: Shoup / Harvey arithmetic (10 IMAD per product), the path any 60-bit prime takes"}
+        eng.close()
+        eng = A.Engine(vlmax_bits=N * 64, spm_rows=2 * rows, ksk_rows=0, device=local, moduli=list(zip(primes, psis)),
+                       l2_chunk_bytes=args.chunk_mib << 20)
+        eng.set_stream(stream.cuda_stream)
+        eng.load_isram(asm.transform_stream(N, primes).words(), 0)
+        eng.load_isram(asm.transform_stream(N, primes, inverse=True).words(), 1024)
+        eng.dma_mem_h2d(0, (host_in.data_ptr(), nbytes))
+        eng.run_vp_batch(0, calls)
+        eng.sync()
+
     extra = {}
     if not args.no_extra:
         eng_kwargs = {"device": local}
@@ -363,10 +401,62 @@ def run_gpu(args):
     ms_e2e = timed(e2e_step, e2e_steps)
     e2e_value = world * ntts_per_step * e2e_steps / (ms_e2e / 1e3)
 
+    # What the host link allows: the same two pinned buffers moved up and down concurrently by plain
+    # cudaMemcpyAsync (torch copies on two streams), no kernels -- the ceiling of any per-step host round trip.
+    dev_in = torch.empty(host_in.numel(), dtype=torch.int64, device="cuda")
+    dev_out = torch.empty(host_in.numel(), dtype=torch.int64, device="cuda")
+    s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def copy_step():
+        with torch.cuda.stream(s_up):
+            dev_in.copy_(host_in, non_blocking=True)
+        with torch.cuda.stream(s_down):
+            host_out2.copy_(dev_out, non_blocking=True)
+        s_up.synchronize()
+        s_down.synchronize()
+    host_out2 = torch.empty(host_in.numel(), dtype=torch.int64).pin_memory()
+    copy_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        copy_step()
+    barrier()
+    copy_s = torch.tensor([(time.perf_counter() - t0) / 3], device="cuda")
+    if world > 1:
+        dist.all_reduce(copy_s, op=dist.ReduceOp.MAX)
+    copy_ms = 1e3 * float(copy_s.item())
+    del dev_in, dev_out, host_out2
+    # The reference's actual flow (top_noaxilite_tb.sv:450-496, 596-638): upload the operands ONCE, run a chain of
+    # ops on resident data, download the result ONCE.  Chain: NTT -> element-wise product with a resident
+    # plaintext -> INTT on every limb (encode_post, mul_plain and their inverse at N = 2^16), 3 kernels' worth of
+    # work per host round trip.
+    chain_depth = 4
+    chain = asm.Program().vsetvl(N)
+    for l, q in enumerate(primes):
+        chain.vsetq(q).vle(0, asm.BASE_SRC0, l * ROWS_PER_POLY).vle(1, asm.BASE_SRC1, l * ROWS_PER_POLY)
+        src = 0
+        for _ in range(chain_depth):
+            chain.vntt(2, src).vfqmul(4, 2, 1).vintt(6, 4)
+            src = 6
+        chain.vse(6, asm.BASE_RSLT, l * ROWS_PER_POLY)
+    eng.load_isram(chain.brk().words(), 2048)
+    chain_calls = [A.Engine.make_args([(b * per_poly, 0, rows + b * per_poly, 0, 0) for b in range(c * cp, (c + 1) * cp)])
+                   for c in range(n_chunks)]          # src1 = row 0: polynomial 0 doubles as the plaintext
+
+    def chain_step():
+        for c in range(n_chunks):
+            eng.dma_mem_h2d_async(c * cp * per_poly, host_in.data_ptr() + c * chunk_bytes, chunk_bytes)
+            eng.run_vp_batch(2048, chain_calls[c])
+            eng.dma_mem_d2h_async(host_out.data_ptr() + c * chunk_bytes, rows + c * cp * per_poly, chunk_bytes)
+        eng.sync()
+    chain_step()
+    ms_chain = timed(chain_step, e2e_steps)
+
     ok = True
     if rank == 0 and world == 1:
         # cpu_baseline leg, part 1: the oracle checks two limb-polys of what was just timed
         from oracle import oracle as O
+        e2e_step()
         got = host_out.numpy().view(np.uint64).reshape(POLYS, LIMBS, N)
         tabs = O.NttTables(N, primes, psis)
         sel = np.array([0, LIMBS - 1])
@@ -392,7 +482,16 @@ def run_gpu(args):
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "limb-NTTs/s", "h2d_bytes_per_step": nbytes,
                     "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e / e2e_steps,
-                    "pipeline": f"{n_chunks} chunks, upload / transform / download overlapped (pinned host memory)"},
+                    "pipeline": f"{n_chunks} chunks, upload / transform / download overlapped (pinned host memory)",
+                    "host_link_ceiling": {"ms_per_step": copy_ms, "what": "the same 1 GiB up + 1 GiB down per GPU as two concurrent plain "
+                                          "cudaMemcpyAsync on the same pinned buffers, no kernels; max over ranks",
+                                          "gb_per_s_each_way": nbytes / copy_ms / 1e6,
+                                          "e2e_fraction_of_ceiling": copy_ms / (ms_e2e / e2e_steps)},
+                    "op_chain": {"value": world * 2 * chain_depth * ntts_per_step * e2e_steps / (ms_chain / 1e3), "unit": "limb-NTTs/s",
+                                 "ms_per_step": ms_chain / e2e_steps, "depth": chain_depth,
+                                 "what": "the reference's flow: operands uploaded once, a chain of ops on resident data (here `depth` rounds of "
+                                         "NTT -> product with a resident plaintext -> INTT per limb), result downloaded once",
+                                 "limb_ntts_per_step_per_gpu": 2 * chain_depth * ntts_per_step}},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -408,6 +507,7 @@ def run_gpu(args):
                                    "<.,1> = pseudo-Mersenne arithmetic, which the workload's prime rule selects)",
                          "algorithmic_bytes_per_limb_ntt": ALG_BYTES_PER_NTT},
             "intt": {"value": inv_value, "unit": "limb-NTTs/s", "ms_per_step": ms_inv / args.steps},
+            "generic_primes": generic,
             "engine_stats": {k: s1[k] - s0[k] for k in s1},
         }
         if burst:
@@ -729,6 +829,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--graphs", action="store_true", help="replay the step as one CUDA graph (ALOHA_F_GRAPHS): takes the host's enqueue cost out")
+    ap.add_argument("--generic", action="store_true", help="force the any-prime (Shoup) arithmetic (ALOHA_F_GENERIC_MODMUL)")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (profiling runs)")
     ap.add_argument("--chunk-mib", type=int, default=0, help="override the engine's L2 chunk size")
     ap.add_argument("--polys", type=int, default=64)

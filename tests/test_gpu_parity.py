@@ -42,11 +42,11 @@ def test_tv_replay_with_asynchronous_dumps(case, flags):
     for row, data in ksk.items():
         eng.dma_ksk_h2d(row, data)
     host = A.HostDriver(eng, "\n".join(entry["program"]), n)
-    for i, key in entry["loads"].items():
-        host.dram_write(O.DRAM_VP_BASE + ops[int(i)].dram_addr, G.pool(key))
     for i, data in enc.items():
         host.set_encoder_output(i, data)
     for _ in range(2):
+        for i, key in entry["loads"].items():          # the programs store their result over their input
+            host.dram_write(O.DRAM_VP_BASE + ops[int(i)].dram_addr, G.pool(key))
         seen = 0
         for i, dumps in enumerate(host.run_all_async()):
             for sub, data, wr in dumps:
