@@ -9,6 +9,7 @@
 // All of them are HBM-bound streams: 16-byte vector accesses, one job table per launch
 // (blockIdx.y = job), grids sized so every SM holds several CTAs.
 #include <atomic>
+#include <cstdlib>
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -195,6 +196,39 @@ __device__ __forceinline__ void aut_tile_body(const Job &job, u32 n, u64 *tile) 
         }
     };
     if (T.log_fb > 8) store(std::true_type{}); else store(std::false_type{});
+}
+
+// The direct variant (aut_plan.hpp aut_direct_slot): the same tiles, but a warp covers a 4 x 8 patch of
+// (point, offset) pairs and every lane moves its element straight from global to global -- short runs on both
+// sides instead of long runs through shared memory; no barrier, half the load/store instructions.
+__global__ void __launch_bounds__(kThreads) vaut_direct_kernel(const AutJob *__restrict__ jobs, u32 n) {
+    const AutJob &job = jobs[blockIdx.y];
+    if (blockIdx.x >= job.plan.ntiles) return;
+    const AutPlan &P = job.plan;
+    const AutTile T = aut_tile(P, blockIdx.x);
+    const u32 slots = 1u << (T.log_jb + T.log_fb);
+    const u64 *__restrict__ src = job.src;
+    u64 *__restrict__ dst = job.dst;
+    const u64 q = job.q;
+    const u32 k2 = (u32)job.k & (2 * n - 1);
+    u64 v[kAutIters];
+    u32 dd[kAutIters];
+#pragma unroll
+    for (int it = 0; it < kAutIters; ++it) {
+        const u32 s = it * kThreads + threadIdx.x;
+        u32 jl, fl;
+        aut_direct_slot(T, s, &jl, &fl);
+        dd[it] = ~0u;
+        if (s < slots && jl < T.jcount && fl < T.fcount) {
+            const u32 i = aut_src(P, T, jl, fl);
+            const u64 x = __ldg(src + i);
+            v[it] = aut_negated(i, k2, n) ? q - x : x;
+            dd[it] = aut_dst(P, T, jl, fl);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < kAutIters; ++it)
+        if (dd[it] != ~0u) dst[dd[it]] = v[it];
 }
 
 __global__ void __launch_bounds__(kThreads) vaut_tiled_kernel(const AutJob *__restrict__ jobs, u32 n) {
@@ -393,7 +427,9 @@ cudaError_t launch_vaut(const PermJob *jobs, u32 njobs, u32 n, cudaStream_t st) 
     return cudaGetLastError();
 }
 cudaError_t launch_vaut_tiled(const AutJob *jobs, u32 njobs, u32 n, u32 max_tiles, cudaStream_t st) {
-    vaut_tiled_kernel<<<dim3(max_tiles, njobs), kThreads, 0, st>>>(jobs, n);
+    static const bool direct = std::getenv("ALOHA_AUT_DIRECT") != nullptr;      // A/B switch for measurements
+    if (direct) vaut_direct_kernel<<<dim3(max_tiles, njobs), kThreads, 0, st>>>(jobs, n);
+    else vaut_tiled_kernel<<<dim3(max_tiles, njobs), kThreads, 0, st>>>(jobs, n);
     ++g_launches;
     return cudaGetLastError();
 }

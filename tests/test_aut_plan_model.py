@@ -24,13 +24,13 @@ def model():
     return C.CDLL(LIB)
 
 
-def apply(model, n, k, q=(1 << 60) - 93, seed=1):
+def apply(model, n, k, q=(1 << 60) - 93, seed=1, fn="aut_model_apply"):
     src = np.random.default_rng(seed).integers(0, q, n, dtype=np.uint64)
     src[:4] = 0                                    # 0 -> q on the negated half
     dst = np.full(n, 0xDEAD, dtype=np.uint64)
     st = (C.c_uint64 * 8)()
-    rc = model.aut_model_apply(C.c_uint32(n), C.c_uint64(k), C.c_uint64(q), src.ctypes.data_as(C.c_void_p),
-                               dst.ctypes.data_as(C.c_void_p), st)
+    rc = getattr(model, fn)(C.c_uint32(n), C.c_uint64(k), C.c_uint64(q), src.ctypes.data_as(C.c_void_p),
+                            dst.ctypes.data_as(C.c_void_p), st)
     assert rc == 0, (n, k, rc)
     i = np.arange(n, dtype=np.uint64)
     d = (i * np.uint64(k)) % np.uint64(n)
@@ -65,6 +65,20 @@ def test_full_size_galois_elements(model):
         assert st[7] <= 1.5 * (2 * n / 32), (k, "warp steps", st[7])
         assert st[5] <= 2 and st[6] <= 2, (k, "shared-memory bank conflicts", st[5], st[6])
     assert worst >= 1.0
+
+
+def test_direct_variant_covers_and_stays_within_sector_budget(model):
+    """the no-shared-memory variant: a warp takes a 4 x 8 patch of (point, offset) pairs"""
+    for n in (256, 4096):
+        for k in list(range(1, 2 * n, 2))[:: max(1, n // 64)] + [2 * n - 1, n + 1, n // 2 + 1]:
+            ok, st = apply(model, n, k, fn="aut_model_direct")
+            assert ok and st[0] == n and st[1] == 0, (n, k, st)
+    n = 65536
+    for k in [pow(3, s, 2 * n) for s in (1, 2, 8, 18, n // 8)] + [2 * n - 1, 12345]:
+        ok, st = apply(model, n, k, fn="aut_model_direct")
+        assert ok and st[0] == n and st[1] == 0
+        # a plain gather touches n + n/4 sectors; the patches stay well below that
+        assert st[2] + st[3] <= 0.8 * (n + n / 4), (k, st[2] / (n / 4), st[3] / (n / 4))
 
 
 def test_python_oracle_agrees(model):

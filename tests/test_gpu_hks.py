@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import aloha_b200 as A
-from aloha_b200 import hks, params
+from aloha_b200 import asm, hks, params
 from oracle import oracle as O
 import test_hks as T
 
@@ -79,6 +79,52 @@ def test_config5_shapes_four_output_limbs_vs_oracle(L, K, dnum):
         del ks, m
     for i in only:
         assert (outs[0][i][0] == outs[1][i][0]).all() and (outs[0][i][1] == outs[1][i][1]).all(), i
+
+
+@pytest.mark.parametrize("bad_iq", [False, True])
+def test_base_extension_chain_on_raw_words(bad_iq):
+    """The fused base-extension kernel against the oracle on words the generated streams never produce: raw
+    64-bit garbage behind VCPY / no pre-op (its lazy fast path must hand those elements to the RTL chain),
+    and a VSETIQ that is not q's Barrett constant (the whole job takes the RTL chain).  Nine terms, so the
+    mid-chain reduction of the lazy sums runs too."""
+    n, rp = 1024, 8
+    q = O.Q0
+    rng = np.random.default_rng(77)
+    nterms = 9
+    x = rng.integers(0, q, (nterms, n), dtype=np.uint64)
+    x[0] = rng.integers(0, 2**64, n, dtype=np.uint64)          # behind VFQMOD: any word is in the domain
+    x[1, ::7] = rng.integers(0, 2**64, len(x[1, ::7]), dtype=np.uint64)   # behind VCPY: some words >= 4q
+    x[2, ::5] += np.uint64(3 * q)                               # behind VCPY: [3q, 4q) is still in the domain
+    x[3, 3::11] = rng.integers(2 * q, 2**64, len(x[3, 3::11]), dtype=np.uint64)  # no pre-op: some words >= 2q
+    scal = [int(v) for v in rng.integers(1, q, nterms)]
+    pre = ["vfqmod", "vcpy", "vcpy", None] + ["vcpy", "vfqmod"] * 3
+    p = asm.Program().vsetvl(n).vsetq(q)
+    if bad_iq:
+        p.buf.append(asm.word(asm.F6["VSETIQ"], imm=asm.barrett_iq(q) ^ 0x5555))
+    for t in range(nterms):
+        p.vle(0, 0, t * rp)
+        src = 0
+        if pre[t]:
+            getattr(p, pre[t])(8, 0)
+            src = 8
+        if t == 0:
+            p.vfqmul(13, src, imm=scal[t])
+        else:
+            p.vfqmul(10, src, imm=scal[t]).vfqadd(13, 13, 10)
+    p.vfqsub(2, 13, imm=12345).vse(2, 2, 0)
+    # a second, throw-away chain redefines v8 / v10 / v13 so that the first one's temporaries are dead
+    p.vle(0, 0, 0).vcpy(8, 0).vfqmul(13, 8, imm=3).vfqmul(10, 8, imm=5).vfqadd(13, 13, 10).vse(13, 2, rp)
+    p.brk()
+    outs = []
+    for m in (O.GoldenModel(vlmax_bits=n * 64, spm_rows=(nterms + 2) * rp, ksk_rows=1, moduli=()),
+              A.Engine(vlmax_bits=n * 64, spm_rows=(nterms + 2) * rp, ksk_rows=1, moduli=())):
+        m.load_isram(p.words(), 0)
+        m.dma_mem_h2d(0, x.reshape(-1))
+        m.run_vp(0, 0, 0, nterms * rp)
+        outs.append(m.dma_mem_d2h(nterms * rp, 2 * n))
+        if isinstance(m, A.Engine):
+            assert m.stats()["ops_fused"] >= 2 * nterms
+    assert (outs[0] == outs[1]).all()
 
 
 def test_rescale_engine_vs_oracle():
