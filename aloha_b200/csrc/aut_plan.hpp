@@ -96,22 +96,6 @@ ALOHA_HD void aut_store_slot(const AutTile &t, uint32_t s, uint32_t *jl, uint32_
     *jl = s >> t.log_fb; *fl = s & ((1u << t.log_fb) - 1);
 }
 
-// ---- the direct variant: no shared memory ----------------------------------------------------------------
-// A warp takes a small (2^a points) x (2^b offsets) sub-rectangle of the tile, a + b = 5: lane = (fl_lo, jl_lo)
-// with jl_lo fastest.  Its load touches 2^b runs of 2^a consecutive source words, its store 2^a runs of 2^b
-// consecutive destination words -- e.g. 4 x 8: eight 32-byte source runs and four 64-byte destination runs per
-// warp instruction, against 32 scattered words on one side for a plain gather.  No barrier, one LDG and one
-// STG per element.
-ALOHA_HD void aut_direct_slot(const AutTile &t, uint32_t s, uint32_t *jl, uint32_t *fl) {
-    const uint32_t a = t.log_jb < 2 ? t.log_jb : (t.log_fb < 3 ? (5 - t.log_fb < t.log_jb ? 5 - t.log_fb : t.log_jb) : 2);
-    const uint32_t b = 5 - a < t.log_fb ? 5 - a : t.log_fb;
-    const uint32_t sub = s & ((1u << (a + b)) - 1), blk = s >> (a + b);
-    const uint32_t jl_lo = sub & ((1u << a) - 1), fl_lo = sub >> a;
-    const uint32_t fblk = blk & ((1u << (t.log_fb - b)) - 1), jblk = blk >> (t.log_fb - b);
-    *jl = (jblk << a) + jl_lo;
-    *fl = (fblk << b) + fl_lo;
-}
-
 // ---- how a thread walks its slots ----------------------------------------------------------------------
 // A thread's slots are kAutThreads apart (slot = it * 256 + tid).  From one slot to the next either the fast
 // coordinate advances by 256 (block side > 256: WIDE; it wraps into the slow one every side / 256 steps, for

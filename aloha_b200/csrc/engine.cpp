@@ -149,14 +149,16 @@ int get_tables(aloha *E, int mod, unsigned logn, const TwTable **out) {
                 inv_rows[r * 256 + row_slot(u, j)] = inv[(1ull << (logn - 8 + u)) + (r << u) + j];
             }
     TwTable t;
-    CU(cudaMalloc(&t.fwd, n * sizeof(Tw)));
-    CU(cudaMalloc(&t.inv, n * sizeof(Tw)));
-    CU(cudaMalloc(&t.fwd_rows, n * sizeof(Tw)));
-    CU(cudaMalloc(&t.inv_rows, n * sizeof(Tw)));
-    CU(cudaMemcpy(t.fwd, fwd.data(), n * sizeof(Tw), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(t.inv, inv.data(), n * sizeof(Tw), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(t.fwd_rows, fwd_rows.data(), n * sizeof(Tw), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(t.inv_rows, inv_rows.data(), n * sizeof(Tw), cudaMemcpyHostToDevice));
+    const struct { Tw **dev; const std::vector<Tw> *host; } parts[4] = {
+        {&t.fwd, &fwd}, {&t.inv, &inv}, {&t.fwd_rows, &fwd_rows}, {&t.inv_rows, &inv_rows}};
+    for (auto &pt : parts) {
+        cudaError_t e = cudaMalloc(pt.dev, n * sizeof(Tw));
+        if (e == cudaSuccess) e = cudaMemcpy(*pt.dev, pt.host->data(), n * sizeof(Tw), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {                 // nothing half-built stays behind
+            cudaFree(t.fwd); cudaFree(t.inv); cudaFree(t.fwd_rows); cudaFree(t.inv_rows);
+            return fail(E, ALOHA_E_CUDA, std::string("twiddle tables: ") + cudaGetErrorString(e));
+        }
+    }
     const u64 ninv = powmod(n % q, q - 2, q);
     const Tw a = twiddle(ninv, q, form), b = twiddle((u64)((u128)inv[1].w * ninv % q), q, form);
     t.mc.q = q;
@@ -694,7 +696,10 @@ size_t fuse_ops(std::vector<VecOp> &ops, const Loc *final_loc, const aloha *E) {
         const int pe = prod_a[i];
         if (pe < 0 || ops[pe].dead || ops[pe].kind != K_EW || ops[pe].q != t.q || ops[pe].n != t.n) continue;
         const VecOp &e = ops[pe];
-        const u32 pre = (e.alu == A_ADDVS && e.s == 0) ? (u32)PRE_VCPY : e.alu == A_MOD ? (u32)PRE_VFQMOD : 0u;
+        u32 pre = (e.alu == A_ADDVS && e.s == 0) ? (u32)PRE_VCPY : e.alu == A_MOD ? (u32)PRE_VFQMOD : 0u;
+        // the transform's load stage computes VFQMOD as an exact x mod q, which is what barrett(r(x), 1) returns
+        // only under q's own Barrett constant: with any other VSETIQ the op stays a separate RTL-exact kernel
+        if (pre == PRE_VFQMOD && e.iq != (u64)((((u128)1) << 121) / e.q)) pre = 0;
         if (!pre || !single_use_temp(pe)) continue;
         bool clobbered = false;
         for (size_t j = pe + 1; j < i && !clobbered; ++j)
@@ -1023,12 +1028,17 @@ int execute_plan(aloha *E, Plan &plan) {
             cudaGraph_t g;
             CU(cudaStreamBeginCapture(E->stream, cudaStreamCaptureModeThreadLocal));
             int rc = issue(E, plan, &launched);
+            g = nullptr;
             cudaError_t ce = cudaStreamEndCapture(E->stream, &g);
-            if (rc) return rc;
-            CU(ce);
+            if (rc || ce != cudaSuccess) {
+                if (g) cudaGraphDestroy(g);
+                if (rc) return rc;
+                CU(ce);
+            }
             plan.kernel_launches = launched;
-            CU(cudaGraphInstantiate(&plan.graph, g, 0));
+            ce = cudaGraphInstantiate(&plan.graph, g, 0);
             cudaGraphDestroy(g);
+            CU(ce);
         }
         CU(cudaGraphLaunch(plan.graph, E->stream));
         launched = plan.kernel_launches;
@@ -1220,9 +1230,11 @@ int cow_for_host_write(aloha *E, u64 off, u64 n) {
     rc = compile_plan(E, B, &plan);
     if (!rc) rc = execute_plan(E, plan);
     if (!rc) {
-        CU(cudaStreamSynchronize(E->stream));
-        commit(E, plan);
+        const cudaError_t se = cudaStreamSynchronize(E->stream);
+        if (se != cudaSuccess) rc = fail(E, ALOHA_E_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(se));
+        else commit(E, plan);
     }
+    if (plan.graph) cudaGraphExecDestroy(plan.graph);
     cudaFree(plan.d_tables);
     return rc;
 }
@@ -1441,7 +1453,10 @@ int aloha_spm_written(aloha_t *E, uint32_t row, uint64_t nwords, uint8_t *out) {
     FLUSH();
     const u64 off = (u64)row * kLanes;
     if (off + nwords > E->spm_words) return fail(E, ALOHA_E_RANGE, "range beyond SPM");
-    for (u64 i = 0; i < nwords; ++i) out[i] = E->written[(off + i) / 8];
+    // one flag per 64-byte beat (8 words); `off` is row-aligned, hence beat-aligned
+    u64 i = 0;
+    for (; i + 8 <= nwords; i += 8) std::memset(out + i, E->written[(off + i) / 8], 8);
+    for (; i < nwords; ++i) out[i] = E->written[(off + i) / 8];
     return ALOHA_OK;
 }
 

@@ -16,38 +16,6 @@ typedef unsigned long long u64;
 
 extern "C" {
 
-// the direct (no shared memory) variant's lane mapping: coverage and sectors per warp instruction
-int aut_model_direct(uint32_t n, u64 k, u64 q, const u64 *src, u64 *dst, u64 stats[8]) {
-    const AutPlan P = make_aut_plan(n, k);
-    std::vector<uint8_t> seen(n, 0);
-    std::memset(stats, 0, 8 * sizeof(u64));
-    const u64 k2 = k & (2ull * n - 1);
-    for (uint32_t tile = 0; tile < P.ntiles; ++tile) {
-        const AutTile T = aut_tile(P, tile);
-        const uint32_t slots = 1u << (T.log_jb + T.log_fb);
-        for (uint32_t base = 0; base < slots; base += 32) {
-            std::set<uint32_t> ssec, dsec;
-            for (uint32_t lane = 0; lane < 32 && base + lane < slots; ++lane) {
-                uint32_t jl, fl;
-                aut_direct_slot(T, base + lane, &jl, &fl);
-                if (jl >= T.jcount || fl >= T.fcount) continue;
-                const uint32_t i = aut_src(P, T, jl, fl), d = aut_dst(P, T, jl, fl);
-                dst[d] = aut_negated(i, (uint32_t)k2, n) ? q - src[i] : src[i];
-                if (seen[d]) ++stats[1];
-                seen[d] = 1;
-                ++stats[0];
-                ssec.insert(i >> 2);
-                dsec.insert(d >> 2);
-            }
-            if (ssec.empty()) continue;
-            ++stats[7];
-            stats[2] += ssec.size();
-            stats[3] += dsec.size();
-        }
-    }
-    return 0;
-}
-
 // out: mask, kmod, kinv, ntiles, then per class: j_begin, j_end, gap, log_jb, log_fb, fblocks, stride, tile_begin
 int aut_model_plan(uint32_t n, u64 k, uint32_t out[22]) {
     const AutPlan p = make_aut_plan(n, k);

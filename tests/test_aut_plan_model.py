@@ -67,20 +67,6 @@ def test_full_size_galois_elements(model):
     assert worst >= 1.0
 
 
-def test_direct_variant_covers_and_stays_within_sector_budget(model):
-    """the no-shared-memory variant: a warp takes a 4 x 8 patch of (point, offset) pairs"""
-    for n in (256, 4096):
-        for k in list(range(1, 2 * n, 2))[:: max(1, n // 64)] + [2 * n - 1, n + 1, n // 2 + 1]:
-            ok, st = apply(model, n, k, fn="aut_model_direct")
-            assert ok and st[0] == n and st[1] == 0, (n, k, st)
-    n = 65536
-    for k in [pow(3, s, 2 * n) for s in (1, 2, 8, 18, n // 8)] + [2 * n - 1, 12345]:
-        ok, st = apply(model, n, k, fn="aut_model_direct")
-        assert ok and st[0] == n and st[1] == 0
-        # a plain gather touches n + n/4 sectors; the patches stay well below that
-        assert st[2] + st[3] <= 0.8 * (n + n / 4), (k, st[2] / (n / 4), st[3] / (n / 4))
-
-
 def test_python_oracle_agrees(model):
     """the same permutation through oracle.automorph (the C++ golden model's VAUT)"""
     from oracle import oracle as O

@@ -44,14 +44,19 @@ def test_tv_replay_with_asynchronous_dumps(case, flags):
     host = A.HostDriver(eng, "\n".join(entry["program"]), n)
     for i, data in enc.items():
         host.set_encoder_output(i, data)
-    for _ in range(2):
+    first_masks = {}
+    for rnd in range(2):
         for i, key in entry["loads"].items():          # the programs store their result over their input
             host.dram_write(O.DRAM_VP_BASE + ops[int(i)].dram_addr, G.pool(key))
         seen = 0
         for i, dumps in enumerate(host.run_all_async()):
             for sub, data, wr in dumps:
                 name = f"inst_{i}_out" if sub is None else f"inst_{i}_{sub}_out"
-                assert G.poly_hashes(data, wr, n) == entry["dumps"][name], f"{case}/{name}"
+                if rnd == 0:
+                    first_masks[name] = wr.copy()
+                # never-written words ('x') only exist the first time round: the second pass checks the values
+                # under the first pass's masks
+                assert G.poly_hashes(data, first_masks[name], n) == entry["dumps"][name], f"{case}/{name}/{rnd}"
                 seen += 1
         assert seen == len(entry["dumps"])
 
