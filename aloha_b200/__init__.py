@@ -66,7 +66,7 @@ EXPORTS = ["aloha_create", "aloha_destroy", "aloha_strerror", "aloha_last_error"
            "aloha_get_stats", "aloha_get_csr", "aloha_decode", "aloha_host_create",
            "aloha_host_destroy", "aloha_host_num_ops", "aloha_host_dram_write", "aloha_host_dram_read",
            "aloha_host_set_encoder_output", "aloha_host_run_op", "aloha_write_dump_text",
-           "aloha_flush", "aloha_pinned_alloc", "aloha_pinned_free", "aloha_host_run_op_async", "aloha_host_sync",
+           "aloha_flush", "aloha_pinned_alloc", "aloha_pinned_free", "aloha_host_run_op_async", "aloha_host_run_range_async", "aloha_host_sync",
            "aloha_group_unique_id", "aloha_group_create", "aloha_group_create_local",
            "aloha_group_destroy", "aloha_group_size", "aloha_group_rank", "aloha_group_last_error",
            "aloha_group_all_gather_rows", "aloha_group_broadcast_rows", "aloha_group_wait"]
@@ -124,6 +124,7 @@ def load_library(rebuild: bool = False) -> C.CDLL:
         "aloha_pinned_alloc": (C.c_int, [u64, C.POINTER(vp)]),
         "aloha_pinned_free": (None, [vp]),
         "aloha_host_run_op_async": (C.c_int, [vp, u32, p64, p8, p64, p8, C.POINTER(C.c_int)]),
+        "aloha_host_run_range_async": (C.c_int, [vp, u32, u32, p64, p8, p64, p8, C.POINTER(C.c_int)]),
         "aloha_host_sync": (C.c_int, [vp]),
         "aloha_group_unique_id": (C.c_int, [p8]),
         "aloha_group_create": (C.c_int, [vp, p8, C.c_int, C.c_int, C.POINTER(vp)]),
@@ -386,7 +387,7 @@ class HostDriver:
             self.h = None
             for p in getattr(self, "_pinned_blocks", []):
                 self.L.aloha_pinned_free(p)
-            self._pinned_blocks, self._dump_pool = [], []
+            self._pinned_blocks, self._dump_pool = [], None
 
     __del__ = close
 
@@ -449,26 +450,22 @@ class HostDriver:
         count = len(self) - first if count is None else count
         w = 4 * self.n
         if not hasattr(self, "_pinned_blocks"):
-            self._pinned_blocks, self._dump_pool = [], []
-        while len(self._dump_pool) < count:
-            self._dump_pool.append((self._pinned(w), self._pinned(w), np.empty(w, np.uint8), np.empty(w, np.uint8)))
-        res = []
-        for n_, i in enumerate(range(first, first + count)):
-            dump, sub, wr, swr = self._dump_pool[n_]
-            has_sub = C.c_int(0)
-            rc = self.L.aloha_host_run_op_async(self.h, i, _p64(dump), _p8(wr), _p64(sub), _p8(swr), C.byref(has_sub))
-            if rc:
-                raise AlohaError(rc, f"host_run_op_async({i})", self.L.aloha_last_error(self.eng.h).decode())
-            res.append((has_sub.value, dump, wr, sub, swr))
-        rc = self.L.aloha_host_sync(self.h)
+            self._pinned_blocks, self._dump_pool = [], None
+        if self._dump_pool is None or self._dump_pool[0].shape[0] < count:
+            self._dump_pool = (self._pinned(count * w).reshape(count, w), self._pinned(count * w).reshape(count, w),
+                               np.empty((count, w), np.uint8), np.empty((count, w), np.uint8), (C.c_int * count)())
+        dumps, subs, wr, swr, has_sub = self._dump_pool
+        rc = self.L.aloha_host_run_range_async(self.h, first, count, _p64(dumps), _p8(wr), _p64(subs), _p8(swr), has_sub)
+        if not rc:
+            rc = self.L.aloha_host_sync(self.h)
         if rc:
-            raise AlohaError(rc, "host_sync", self.L.aloha_last_error(self.eng.h).decode())
+            raise AlohaError(rc, "host_run_range_async", self.L.aloha_last_error(self.eng.h).decode())
         out = []
-        for has_sub, dump, wr, sub, swr in res:
+        for j in range(count):
             ops = []
-            if has_sub:
-                ops.append((0, sub, swr.astype(bool)))
-            ops.append((None, dump, wr.astype(bool)))
+            if has_sub[j]:
+                ops.append((0, subs[j], swr[j].view(bool)))
+            ops.append((None, dumps[j], wr[j].view(bool)))
             out.append(ops)
         return out
 

@@ -44,7 +44,12 @@ namespace alb {
 constexpr unsigned kAutTileLog = ALOHA_AUT_TILE_LOG;  // 2048 words = 16 KiB per tile
 constexpr unsigned kAutTile = 1u << kAutTileLog;
 constexpr unsigned kAutSmemWords = kAutTile + 1024;  // worst-case padding: FB rows * 1 word (FB <= 1024)
-constexpr unsigned kAutThreads = 256;
+#ifndef ALOHA_AUT_THREADS
+#define ALOHA_AUT_THREADS 256
+#endif
+constexpr unsigned kAutThreads = ALOHA_AUT_THREADS;    // threads per CTA of the tiled kernels (a thread's slots are this far apart)
+constexpr unsigned kAutThreadsLog = kAutThreads == 128 ? 7 : kAutThreads == 256 ? 8 : kAutThreads == 512 ? 9 : 10;
+static_assert((1u << kAutThreadsLog) == kAutThreads, "128, 256, 512 or 1024 threads");
 
 struct AutClass {
     uint32_t j_begin, j_end;   // points of this class

@@ -144,101 +144,70 @@ __global__ void __launch_bounds__(kThreads) autmac_kernel(const AutMacJob *__res
 // consecutive DESTINATION words (and, fused, reads p and c along the same runs).  Both sides of the
 // permutation move in 128-byte lines; the transposition is the padded shared-memory tile.
 // Same per-element function as the gather kernels: raw q - x on the negated half ((i*k) mod 2n >= n).
-constexpr int kAutIters = kAutTile / kThreads;      // 8 slots per thread
-static_assert(kThreads == (int)kAutThreads, "aut_plan.hpp replays the kernels with this block size");
+constexpr int kAutIters = kAutTile / kAutThreads;   // slots per thread
 
 // Index arithmetic is incremental (aut_plan.hpp AutLoadWalk / AutStoreWalk, the same code the CPU model in
 // tests/native replays): per-CTA constant steps, aut_src / aut_dst evaluated once per thread.
-// A CTA walks kAutTilesPerCta consecutive tiles of one job through two shared-memory buffers: the loads of
-// tile t+1 (cp.async) are in flight while tile t is stored, so neither the barrier between the phases nor the
-// job-record fetch at the head of the CTA is paid per tile.
-#ifndef ALOHA_AUT_TILES_PER_CTA
-#define ALOHA_AUT_TILES_PER_CTA 4
-#endif
-constexpr int kAutTilesPerCta = ALOHA_AUT_TILES_PER_CTA;
-
-template <class Job>
-struct AutCtx {
-    const AutPlan &P;
-    const u64 *__restrict__ src;
-    u64 *__restrict__ dst;
-    const u64 *__restrict__ pp, *__restrict__ cc;
-    u64 q, iq;
-    u32 k2, n;
-};
-
 template <bool MAC, class Job>
-__device__ __forceinline__ void aut_issue_loads(const AutCtx<Job> &C, const AutTile &T, u64 *tile) {
+__device__ __forceinline__ void aut_tile_body(const Job &job, u32 n, u64 *tile) {
+    const AutPlan &P = job.plan;
+    const AutTile T = aut_tile(P, blockIdx.x);
+    const u64 *__restrict__ src;
+    if constexpr (MAC) src = job.x; else src = job.src;
+    u64 *__restrict__ dst = job.dst;
+    const u64 q = job.q;
+    const u32 k2 = (u32)job.k & (2 * n - 1);
+    // ---- load: cp.async (LDGSTS) straight into the tile, lanes along the source
     auto load = [&](auto wide) {
-        AutLoadWalk<decltype(wide)::value> w(C.P, T, threadIdx.x);
+        AutLoadWalk<decltype(wide)::value> w(P, T, threadIdx.x);
         if (w.idle()) return;
         const u32 tile_addr = (u32)__cvta_generic_to_shared(tile);
 #pragma unroll
         for (int it = 0; it < kAutIters; ++it) {
             if (w.valid())
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile_addr + w.sm * 8), "l"(C.src + w.i) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile_addr + w.sm * 8), "l"(src + w.i) : "memory");
             w.next();
         }
     };
-    if (T.log_jb > 8) load(std::true_type{}); else load(std::false_type{});
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-template <bool MAC, class Job>
-__device__ __forceinline__ void aut_store_tile(const AutCtx<Job> &C, const AutTile &T, const u64 *tile) {
+    if (T.log_jb > kAutThreadsLog) load(std::true_type{}); else load(std::false_type{});
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    // ---- store: lanes along the destination
     auto store = [&](auto wide) {
-        AutStoreWalk<decltype(wide)::value> w(C.P, T, threadIdx.x);
+        AutStoreWalk<decltype(wide)::value> w(P, T, threadIdx.x);
         if (w.idle()) return;
+        [[maybe_unused]] const u64 *__restrict__ pp = nullptr, *__restrict__ cc = nullptr;
+        [[maybe_unused]] u64 iq = 0;
+        if constexpr (MAC) { pp = job.p; cc = job.c; iq = job.iq; }
 #pragma unroll
         for (int it = 0; it < kAutIters; ++it) {
             if (w.valid()) {
                 const u64 x = tile[w.sm];
-                const u64 y = aut_negated(w.i, C.k2, C.n) ? C.q - x : x;
+                const u64 y = aut_negated(w.i, k2, n) ? q - x : x;
                 if constexpr (MAC) {
-                    const u64 m = rtl_alu<ALU_MUL_VV>(y, C.pp[w.d], 0, C.q, C.iq);
-                    C.dst[w.d] = rtl_alu<ALU_ADD_VV>(C.cc[w.d], m, 0, C.q, C.iq);
+                    const u64 m = rtl_alu<ALU_MUL_VV>(y, pp[w.d], 0, q, iq);
+                    dst[w.d] = rtl_alu<ALU_ADD_VV>(cc[w.d], m, 0, q, iq);
                 } else {
-                    C.dst[w.d] = y;
+                    dst[w.d] = y;
                 }
             }
             w.next();
         }
     };
-    if (T.log_fb > 8) store(std::true_type{}); else store(std::false_type{});
+    if (T.log_fb > kAutThreadsLog) store(std::true_type{}); else store(std::false_type{});
 }
 
-template <bool MAC, class Job>
-__device__ __forceinline__ void aut_cta(const Job &job, u32 n, u64 (*tiles)[kAutSmemWords]) {
-    const u32 first = blockIdx.x * kAutTilesPerCta;
-    if (first >= job.plan.ntiles) return;
-    const u32 count = job.plan.ntiles - first < (u32)kAutTilesPerCta ? job.plan.ntiles - first : (u32)kAutTilesPerCta;
-    AutCtx<Job> C{job.plan, nullptr, job.dst, nullptr, nullptr, job.q, 0, (u32)job.k & (2 * n - 1), n};
-    if constexpr (MAC) { C.src = job.x; C.pp = job.p; C.cc = job.c; C.iq = job.iq; }
-    else C.src = job.src;
-    AutTile next = aut_tile(C.P, first);
-    aut_issue_loads<MAC>(C, next, tiles[0]);
-    for (u32 t = 0; t < count; ++t) {
-        const AutTile cur = next;
-        if (t + 1 < count) {
-            next = aut_tile(C.P, first + t + 1);
-            aut_issue_loads<MAC>(C, next, tiles[(t + 1) & 1]);      // its buffer was drained two iterations ago
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();                                            // tile t has landed for every thread
-        aut_store_tile<MAC>(C, cur, tiles[t & 1]);
-        __syncthreads();                                            // nobody still reads buffer t & 1 when it is refilled
-    }
+__global__ void __launch_bounds__(kAutThreads) vaut_tiled_kernel(const AutJob *__restrict__ jobs, u32 n) {
+    __shared__ u64 tile[kAutSmemWords];
+    const AutJob &job = jobs[blockIdx.y];
+    if (blockIdx.x >= job.plan.ntiles) return;
+    aut_tile_body<false>(job, n, tile);
 }
-
-__global__ void __launch_bounds__(kThreads) vaut_tiled_kernel(const AutJob *__restrict__ jobs, u32 n) {
-    __shared__ u64 tiles[2][kAutSmemWords];
-    aut_cta<false>(jobs[blockIdx.y], n, tiles);
-}
-__global__ void __launch_bounds__(kThreads) autmac_tiled_kernel(const AutMacJob *__restrict__ jobs, u32 n) {
-    __shared__ u64 tiles[2][kAutSmemWords];
-    aut_cta<true>(jobs[blockIdx.y], n, tiles);
+__global__ void __launch_bounds__(kAutThreads) autmac_tiled_kernel(const AutMacJob *__restrict__ jobs, u32 n) {
+    __shared__ u64 tile[kAutSmemWords];
+    const AutMacJob &job = jobs[blockIdx.y];
+    if (blockIdx.x >= job.plan.ntiles) return;
+    aut_tile_body<true>(job, n, tile);
 }
 
 // dst = c + a*b : product and sum exactly as VFQMUL.vv then VFQADD.vv would store them
@@ -424,12 +393,12 @@ cudaError_t launch_vaut(const PermJob *jobs, u32 njobs, u32 n, cudaStream_t st) 
     return cudaGetLastError();
 }
 cudaError_t launch_vaut_tiled(const AutJob *jobs, u32 njobs, u32 n, u32 max_tiles, cudaStream_t st) {
-    vaut_tiled_kernel<<<dim3((max_tiles + kAutTilesPerCta - 1) / kAutTilesPerCta, njobs), kThreads, 0, st>>>(jobs, n);
+    vaut_tiled_kernel<<<dim3(max_tiles, njobs), kAutThreads, 0, st>>>(jobs, n);
     ++g_launches;
     return cudaGetLastError();
 }
 cudaError_t launch_autmac_tiled(const AutMacJob *jobs, u32 njobs, u32 n, u32 max_tiles, cudaStream_t st) {
-    autmac_tiled_kernel<<<dim3((max_tiles + kAutTilesPerCta - 1) / kAutTilesPerCta, njobs), kThreads, 0, st>>>(jobs, n);
+    autmac_tiled_kernel<<<dim3(max_tiles, njobs), kAutThreads, 0, st>>>(jobs, n);
     ++g_launches;
     return cudaGetLastError();
 }

@@ -210,6 +210,22 @@ int aloha_host_run_op_async(aloha_host_t *H, uint32_t i, uint64_t *dump, uint8_t
     return aloha_spm_written(E, op.spm_addr, words, written);
 }
 
+// Ops [first, first + count) in one call: op first + j uses dumps + j*4n, written + j*4n, sub_dumps + j*4n,
+// sub_written + j*4n and has_sub[j].  (The per-op loop of run(), top_noaxilite_tb.sv:596-638, on this side of
+// the boundary: a caller in another language pays one FFI crossing per program, not per op.)
+int aloha_host_run_range_async(aloha_host_t *H, uint32_t first, uint32_t count, uint64_t *dumps, uint8_t *written,
+                               uint64_t *sub_dumps, uint8_t *sub_written, int *has_sub) {
+    if (!H || (uint64_t)first + count > H->ops.size() || !dumps || !written || !sub_dumps || !sub_written || !has_sub)
+        return ALOHA_E_ARG;
+    const uint64_t w = 4ull * H->n;
+    for (uint32_t j = 0; j < count; ++j) {
+        int rc = aloha_host_run_op_async(H, first + j, dumps + j * w, written + j * w, sub_dumps + j * w, sub_written + j * w,
+                                         has_sub + j);
+        if (rc) return rc;
+    }
+    return ALOHA_OK;
+}
+
 int aloha_host_run_op(aloha_host_t *H, uint32_t i, uint64_t *dump, uint8_t *written, uint64_t *sub_dump,
                       uint8_t *sub_written, int *has_sub) {
     if (!H || i >= H->ops.size()) return ALOHA_E_ARG;

@@ -231,6 +231,10 @@ int aloha_host_run_op(aloha_host_t *, uint32_t op_index, uint64_t *dump, uint8_t
  * aloha_host_sync.  The written masks are filled in immediately. */
 int aloha_host_run_op_async(aloha_host_t *, uint32_t op_index, uint64_t *dump, uint8_t *written,
                             uint64_t *sub_dump, uint8_t *sub_written, int *has_sub);
+/* ops [first, first+count) in one call; op first+j uses dumps + j*4n, written + j*4n, sub_dumps + j*4n,
+ * sub_written + j*4n and has_sub[j] */
+int aloha_host_run_range_async(aloha_host_t *, uint32_t first, uint32_t count, uint64_t *dumps, uint8_t *written,
+                               uint64_t *sub_dumps, uint8_t *sub_written, int *has_sub);
 int aloha_host_sync(aloha_host_t *);
 /* "%0d" per line, 'x' for never-written words (dump_poly, top_noaxilite_tb.sv:536-565) */
 int aloha_write_dump_text(const char *path, const uint64_t *data, const uint8_t *written,

@@ -52,11 +52,11 @@ int aut_model_apply(uint32_t n, u64 k, u64 q, const u64 *src, u64 *dst, u64 stat
                         w.next();
                     }
                 };
-                if (phase == 0) { if (T.log_jb > 8) walk(AutLoadWalk<true>(P, T, tid)); else walk(AutLoadWalk<false>(P, T, tid)); }
-                else { if (T.log_fb > 8) walk(AutStoreWalk<true>(P, T, tid)); else walk(AutStoreWalk<false>(P, T, tid)); }
+                if (phase == 0) { if (T.log_jb > kAutThreadsLog) walk(AutLoadWalk<true>(P, T, tid)); else walk(AutLoadWalk<false>(P, T, tid)); }
+                else { if (T.log_fb > kAutThreadsLog) walk(AutStoreWalk<true>(P, T, tid)); else walk(AutStoreWalk<false>(P, T, tid)); }
             }
             for (int it = 0; it < (int)(kAutTile / kAutThreads); ++it)
-                for (uint32_t warp = 0; warp < 8; ++warp) {
+                for (uint32_t warp = 0; warp < kAutThreads / 32; ++warp) {
                     std::set<uint32_t> sectors;
                     uint32_t bank[2][16] = {};
                     bool active = false;
