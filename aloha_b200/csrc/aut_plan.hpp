@@ -245,7 +245,10 @@ inline double finish(AutPlan &p) {
         AutClass best = p.cls[c];
         double best_cost = -1;
         uint32_t last_fb = ~0u;
-        for (uint32_t want = 3; want <= 10; ++want) {
+#ifndef ALOHA_AUT_MIN_LOG_FB
+#define ALOHA_AUT_MIN_LOG_FB 3
+#endif
+        for (uint32_t want = ALOHA_AUT_MIN_LOG_FB; want <= 10; ++want) {
             shape_class(p.cls[c], want);
             if (p.cls[c].log_fb == last_fb) continue;          // clamped to the same shape as before
             last_fb = p.cls[c].log_fb;

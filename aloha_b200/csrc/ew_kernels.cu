@@ -149,9 +149,9 @@ constexpr int kAutIters = kAutTile / kAutThreads;   // slots per thread
 // Index arithmetic is incremental (aut_plan.hpp AutLoadWalk / AutStoreWalk, the same code the CPU model in
 // tests/native replays): per-CTA constant steps, aut_src / aut_dst evaluated once per thread.
 template <bool MAC, class Job>
-__device__ __forceinline__ void aut_tile_body(const Job &job, u32 n, u64 *tile) {
+__device__ __forceinline__ void aut_tile_body(const Job &job, u32 n, u64 *tile, u32 tile_index) {
     const AutPlan &P = job.plan;
-    const AutTile T = aut_tile(P, blockIdx.x);
+    const AutTile T = aut_tile(P, tile_index);
     const u64 *__restrict__ src;
     if constexpr (MAC) src = job.x; else src = job.src;
     u64 *__restrict__ dst = job.dst;
@@ -197,17 +197,51 @@ __device__ __forceinline__ void aut_tile_body(const Job &job, u32 n, u64 *tile) 
     if (T.log_fb > kAutThreadsLog) store(std::true_type{}); else store(std::false_type{});
 }
 
+// The permuted side of the transfer reaches DRAM as 256-byte pieces scattered over the polynomial, which costs
+// row-buffer locality (both aut kernels top out near 0.64 of the streaming copy rate).  So every CTA first asks
+// L2 for a CONTIGUOUS slice of the source of a job kAutPrefetchJobs further down the launch: by the time that
+// job's CTAs run, DRAM has delivered their polynomial in long bursts and their scattered runs hit L2.
+#ifndef ALOHA_AUT_PREFETCH_JOBS
+#define ALOHA_AUT_PREFETCH_JOBS 32
+#endif
+constexpr u32 kAutPrefetchJobs = ALOHA_AUT_PREFETCH_JOBS;
+
+template <class Job>
+__device__ __forceinline__ void aut_prefetch_ahead(const Job *__restrict__ jobs, u32 n, const u64 *Job::*field) {
+    if (kAutPrefetchJobs == 0 || blockIdx.y + kAutPrefetchJobs >= gridDim.y) return;
+    const Job &ahead = jobs[blockIdx.y + kAutPrefetchJobs];
+    const u32 lines = n / 16, per = (lines + gridDim.x - 1) / gridDim.x, l0 = blockIdx.x * per;
+    const u64 *base = ahead.*field;
+    for (u32 l = l0 + threadIdx.x; l < l0 + per && l < lines; l += kAutThreads)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 16 * (size_t)l));
+}
+
+// A CTA may walk kAutTilesPerCta consecutive tiles of its job one after the other (the fetch of the job record
+// that every data load depends on is then paid once per CTA instead of once per tile).  Measured on B200 with
+// 1, 2, 4, 8, 16: one tile per CTA is the fastest (0.65 of the HBM copy rate; 4: 0.53-0.65, 16: 0.41-0.65) --
+// fewer, longer CTAs per polynomial lose more to imbalance than the head costs.  Kept as a build-time knob.
+#ifndef ALOHA_AUT_TILES_PER_CTA
+#define ALOHA_AUT_TILES_PER_CTA 1
+#endif
+constexpr u32 kAutTilesPerCta = ALOHA_AUT_TILES_PER_CTA;
+
+template <bool MAC, class Job>
+__device__ __forceinline__ void aut_cta(const Job &job, u32 n, u64 *tile) {
+    const u32 first = blockIdx.x * kAutTilesPerCta, ntiles = job.plan.ntiles;
+    for (u32 t = first; t < first + kAutTilesPerCta && t < ntiles; ++t) {
+        if (t != first) __syncthreads();                 // the previous tile's store phase still reads the buffer
+        aut_tile_body<MAC>(job, n, tile, t);
+    }
+}
+
 __global__ void __launch_bounds__(kAutThreads) vaut_tiled_kernel(const AutJob *__restrict__ jobs, u32 n) {
     __shared__ u64 tile[kAutSmemWords];
-    const AutJob &job = jobs[blockIdx.y];
-    if (blockIdx.x >= job.plan.ntiles) return;
-    aut_tile_body<false>(job, n, tile);
+    aut_prefetch_ahead(jobs, n, &AutJob::src);
+    aut_cta<false>(jobs[blockIdx.y], n, tile);
 }
 __global__ void __launch_bounds__(kAutThreads) autmac_tiled_kernel(const AutMacJob *__restrict__ jobs, u32 n) {
     __shared__ u64 tile[kAutSmemWords];
-    const AutMacJob &job = jobs[blockIdx.y];
-    if (blockIdx.x >= job.plan.ntiles) return;
-    aut_tile_body<true>(job, n, tile);
+    aut_cta<true>(jobs[blockIdx.y], n, tile);
 }
 
 // dst = c + a*b : product and sum exactly as VFQMUL.vv then VFQADD.vv would store them
@@ -393,12 +427,12 @@ cudaError_t launch_vaut(const PermJob *jobs, u32 njobs, u32 n, cudaStream_t st) 
     return cudaGetLastError();
 }
 cudaError_t launch_vaut_tiled(const AutJob *jobs, u32 njobs, u32 n, u32 max_tiles, cudaStream_t st) {
-    vaut_tiled_kernel<<<dim3(max_tiles, njobs), kAutThreads, 0, st>>>(jobs, n);
+    vaut_tiled_kernel<<<dim3((max_tiles + kAutTilesPerCta - 1) / kAutTilesPerCta, njobs), kAutThreads, 0, st>>>(jobs, n);
     ++g_launches;
     return cudaGetLastError();
 }
 cudaError_t launch_autmac_tiled(const AutMacJob *jobs, u32 njobs, u32 n, u32 max_tiles, cudaStream_t st) {
-    autmac_tiled_kernel<<<dim3(max_tiles, njobs), kAutThreads, 0, st>>>(jobs, n);
+    autmac_tiled_kernel<<<dim3((max_tiles + kAutTilesPerCta - 1) / kAutTilesPerCta, njobs), kAutThreads, 0, st>>>(jobs, n);
     ++g_launches;
     return cudaGetLastError();
 }

@@ -110,6 +110,37 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(gpu: int):
+    """Pin this rank to the CPU cores nearest its GPU (nvidia-smi topo) BEFORE it allocates page-locked host
+    memory, so the staging buffers of the end-to-end path are first-touched on the GPU's own NUMA node instead
+    of all ranks' buffers landing on one memory controller.  Returns the affinity string, or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        hdr = None
+        for line in out.splitlines():
+            cols = line.split("\t")
+            if hdr is None and "CPU Affinity" in line:
+                hdr = [c.strip() for c in cols]
+                continue
+            if hdr and cols and cols[0].strip() == f"GPU{gpu}":
+                idx = hdr.index("CPU Affinity")
+                spec = cols[idx].strip() if idx < len(cols) else ""
+                cores = set()
+                for part in spec.split(","):
+                    if "-" in part:
+                        a, b = part.split("-")
+                        cores.update(range(int(a), int(b) + 1))
+                    elif part.strip().isdigit():
+                        cores.add(int(part))
+                cores &= os.sched_getaffinity(0)
+                if cores:
+                    os.sched_setaffinity(0, cores)
+                    return spec
+    except Exception:
+        pass
+    return None
+
+
 def workload_params():
     from aloha_b200 import params
     primes = params.synthetic_primes(LIMBS, 2 * N)
@@ -197,6 +228,7 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -513,7 +545,7 @@ def run_gpu(args):
         if burst:
             line["burst"] = burst
         if world > 1:
-            line["per_rank"] = {"ms_timed_region": per_rank_ms}
+            line["per_rank"] = {"ms_timed_region": per_rank_ms, "cpu_affinity_of_rank0": numa}
         line.update(extra)
         if world == 1:
             line["cpu_baseline"] = {"value": cpu_all, "unit": "limb-NTTs/s", "cores": cores, "kind": "port",
@@ -611,6 +643,8 @@ def galois_elements():
     ks = [("3^1", pow(3, 1, 2 * N)), ("3^2", pow(3, 2, 2 * N)), ("3^8", pow(3, 8, 2 * N)), ("3^(N/8)", pow(3, N // 8, 2 * N)),
           ("3^18", pow(3, 18, 2 * N))]
     assert any(k >= N and k % N != 1 for _, k in ks)
+    if os.environ.get("ALOHA_BENCH_GALOIS"):        # experiments: "name:k,name:k"
+        ks = [(a.split(":")[0], int(a.split(":")[1])) for a in os.environ["ALOHA_BENCH_GALOIS"].split(",")]
     return ks
 
 
