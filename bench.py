@@ -33,6 +33,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the timed CPU reference is compiled -O3 -march=native on the machine that times it
+os.environ.setdefault("ALOHA_ORACLE_NATIVE", "1")
 
 N = 65536
 LIMBS = 32
@@ -472,14 +474,16 @@ def run_gpu(args):
             src = 6
         chain.vse(6, asm.BASE_RSLT, l * ROWS_PER_POLY)
     eng.load_isram(chain.brk().words(), 2048)
-    chain_calls = [A.Engine.make_args([(b * per_poly, 0, rows + b * per_poly, 0, 0) for b in range(c * cp, (c + 1) * cp)])
-                   for c in range(n_chunks)]          # src1 = row 0: polynomial 0 doubles as the plaintext
+    cn = 4 if POLYS % 4 == 0 else 1                   # fewer, larger chunks: every launch of the chain fills the GPU
+    ccp, cbytes = POLYS // cn, POLYS // cn * LIMBS * N * 8
+    chain_calls = [A.Engine.make_args([(b * per_poly, 0, rows + b * per_poly, 0, 0) for b in range(c * ccp, (c + 1) * ccp)])
+                   for c in range(cn)]                # src1 = row 0: polynomial 0 doubles as the plaintext
 
     def chain_step():
-        for c in range(n_chunks):
-            eng.dma_mem_h2d_async(c * cp * per_poly, host_in.data_ptr() + c * chunk_bytes, chunk_bytes)
+        for c in range(cn):
+            eng.dma_mem_h2d_async(c * ccp * per_poly, host_in.data_ptr() + c * cbytes, cbytes)
             eng.run_vp_batch(2048, chain_calls[c])
-            eng.dma_mem_d2h_async(host_out.data_ptr() + c * chunk_bytes, rows + c * cp * per_poly, chunk_bytes)
+            eng.dma_mem_d2h_async(host_out.data_ptr() + c * cbytes, rows + c * ccp * per_poly, cbytes)
         eng.sync()
     chain_step()
     ms_chain = timed(chain_step, e2e_steps)

@@ -33,10 +33,24 @@ KSK_DRAM_BASE = 524288         # vivado_prj/top_noaxilite.xpr:1448-1450
 
 
 def build(force: bool = False) -> str:
+    """ALOHA_ORACLE_NATIVE=1 (set by bench.py's CPU legs): the -march=native build, compiled on this machine."""
+    native = bool(os.environ.get("ALOHA_ORACLE_NATIVE"))
+    path = os.path.join(_HERE, "libaloha_oracle_native.so") if native else _LIB_PATH
     src = [os.path.join(_HERE, f) for f in ("golden_model.cpp", "golden_model.h", "Makefile")]
-    if force or not os.path.exists(_LIB_PATH) or any(
-            os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src):
-        subprocess.check_call(["make", "-s", "-C", _HERE, "-B" if force else "-s"])
+    if force or not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in src):
+        try:
+            subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []) + (["native"] if native else []))
+        except Exception:
+            if not native:
+                raise
+            path = build_portable()
+    return path
+
+
+def build_portable() -> str:
+    src = [os.path.join(_HERE, f) for f in ("golden_model.cpp", "golden_model.h", "Makefile")]
+    if not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src):
+        subprocess.check_call(["make", "-s", "-C", _HERE])
     return _LIB_PATH
 
 
@@ -46,8 +60,7 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        build()
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(build())
         u64, u32, p64, p8, p32, vp = (C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.c_void_p)
         sig = {
