@@ -298,8 +298,11 @@ class TorchComm:
 
 class KeySwitch:
     """Runs the three phases on one machine (anything with the Engine method set) of a group.
-    overlap: phase 2 is cut by the rank that owns each digit's limbs; the all-gather moves one source rank at
-    a time and the machine starts on the digits that have arrived (its own first)."""
+    overlap: False -- phase 2 waits for the whole all-gather;
+             "own" -- phase 2 is cut in two: the digits this machine produced itself (no wait: they run under the
+                      all-gather), then all the others;
+             "chunks" (or True) -- phase 2 is cut by the rank that owns each digit's limbs; the all-gather moves one
+                      source rank at a time and the machine consumes the blocks as they arrive (its own first)."""
 
     def __init__(self, machine, lay: Layout, comm=None, pc_base: int = 0, overlap: bool = False, lockstep: bool = False):
         """lockstep: every rank consumes the chunks in the same order and waits for each of them, its own
@@ -307,7 +310,7 @@ class KeySwitch:
         self.machine, self.lay, self.comm, self.lockstep = machine, lay, comm or LocalComm(), lockstep
         assert self.comm.world == lay.world and self.comm.rank == lay.rank
         prm = lay.prm
-        self.overlap = overlap and lay.world > 1
+        self.overlap = ("chunks" if overlap is True else overlap) if lay.world > 1 else False
         # digits whose source limbs all live on rank r can be consumed as soon as r's block has arrived;
         # a digit that straddles two ranks waits for the later one
         self.digit_rank = [max(lay.owner(j) for j in g) for g in prm.groups]
@@ -329,16 +332,24 @@ class KeySwitch:
             else:
                 order = self.chunk_order()
                 for n_, r in enumerate(order):
-                    gs = [b for b in range(prm.dnum) if self.digit_rank[b] == r]
-                    put(self.pc2, (t, r), phase2_stream(lay, t, gs, first=n_ == 0, last=n_ == len(order) - 1))
+                    put(self.pc2, (t, r), phase2_stream(lay, t, self.chunk_digits(r), first=n_ == 0, last=n_ == len(order) - 1))
         self.pc_end = pc
 
     def chunk_order(self) -> list[int]:
-        """source ranks in the order phase 2 consumes them: own digits first, then the order of arrival"""
+        """Chunks of phase 2 in the order they run.  "chunks": one per source rank, own digits first, then the
+        order of arrival (lockstep: rank order for everyone).  "own": this rank's digits, then -1 = all the others."""
         have = sorted({r for r in self.digit_rank})
+        if self.overlap == "own":
+            mine = [r for r in have if r == self.lay.rank]
+            return mine + ([-1] if len(have) > len(mine) else [])
         if self.lockstep:
             return have
         return [r for r in have if r == self.lay.rank] + [r for r in have if r != self.lay.rank]
+
+    def chunk_digits(self, r: int) -> list[int]:
+        if r == -1:
+            return [b for b in range(self.lay.prm.dnum) if self.digit_rank[b] != self.lay.rank]
+        return [b for b in range(self.lay.prm.dnum) if self.digit_rank[b] == r]
 
     def load_ksk(self, t: int, data: np.ndarray):
         """data: KSK[t] = 2 dnum polynomials ([b][c] order) under modulus t; only the owner stores it."""
@@ -368,14 +379,14 @@ class KeySwitch:
         reg = lay.region
         ops = [("run", [(self.pc1[j], reg("IN", b), reg("S", b), reg("OUT", b), 0, galois_k)
                         for b in range(B) for j in mine if j < prm.L])]
-        ops.append(("all_gather", lay.S, lay.per_rank * rp, B, lay.S_size, self.overlap))
+        ops.append(("all_gather", lay.S, lay.per_rank * rp, B, lay.S_size, self.overlap == "chunks"))
         if not self.overlap:
             ops.append(("wait", -1))
             ops.append(("run", [(self.pc2[t, None], reg("S", b), reg("OUT", b), reg("ACC", b), lay.ksk_ptr(t), 0)
                                 for b in range(B) for t in mine if want(t)]))
         else:
             for r in self.chunk_order():
-                if r != lay.rank or self.lockstep:
+                if r != lay.rank or (self.lockstep and self.overlap == "chunks"):
                     ops.append(("wait", r))
                 ops.append(("run", [(self.pc2[t, r], reg("S", b), reg("OUT", b), reg("ACC", b), lay.ksk_ptr(t), 0)
                                     for b in range(B) for t in mine if want(t)]))

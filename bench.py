@@ -274,8 +274,10 @@ def run_gpu(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    # renaming pool: the op chain of the end-to-end leg keeps ~3 live temporaries per limb of a 16-polynomial chunk
     eng = A.Engine(vlmax_bits=N * 64, spm_rows=2 * rows, ksk_rows=0, device=local, moduli=list(zip(primes, psis)),
-                   l2_chunk_bytes=args.chunk_mib << 20, flags=(A.F_GRAPHS if args.graphs else 0) | (A.F_GENERIC_MODMUL if args.generic else 0))
+                   l2_chunk_bytes=args.chunk_mib << 20, pool_buffers=4096,
+                   flags=(A.F_GRAPHS if args.graphs else 0) | (A.F_GENERIC_MODMUL if args.generic else 0))
     # A dedicated non-default torch stream: the engine launches on it (aloha_set_stream) and the CUDA
     # events below are recorded on it.  (Stream handle 0 would mean "the engine's own stream".)
     stream = torch.cuda.Stream()
@@ -395,7 +397,7 @@ def run_gpu(args):
                    "note": "same primes, ALOHA_F_GENERIC_MODMUL: Shoup / Harvey arithmetic (10 IMAD per product), the path any 60-bit prime takes"}
         eng.close()
         eng = A.Engine(vlmax_bits=N * 64, spm_rows=2 * rows, ksk_rows=0, device=local, moduli=list(zip(primes, psis)),
-                       l2_chunk_bytes=args.chunk_mib << 20)
+                       l2_chunk_bytes=args.chunk_mib << 20, pool_buffers=4096)
         eng.set_stream(stream.cuda_stream)
         eng.load_isram(asm.transform_stream(N, primes).words(), 0)
         eng.load_isram(asm.transform_stream(N, primes, inverse=True).words(), 1024)
@@ -486,7 +488,9 @@ def run_gpu(args):
             eng.dma_mem_d2h_async(host_out.data_ptr() + c * cbytes, rows + c * ccp * per_poly, cbytes)
         eng.sync()
     chain_step()
+    sc0 = eng.stats()
     ms_chain = timed(chain_step, e2e_steps)
+    chain_launches = (eng.stats()["kernel_launches"] - sc0["kernel_launches"]) / e2e_steps
 
     ok = True
     if rank == 0 and world == 1:
@@ -524,7 +528,7 @@ def run_gpu(args):
                                           "gb_per_s_each_way": nbytes / copy_ms / 1e6,
                                           "e2e_fraction_of_ceiling": copy_ms / (ms_e2e / e2e_steps)},
                     "op_chain": {"value": world * 2 * chain_depth * ntts_per_step * e2e_steps / (ms_chain / 1e3), "unit": "limb-NTTs/s",
-                                 "ms_per_step": ms_chain / e2e_steps, "depth": chain_depth,
+                                 "ms_per_step": ms_chain / e2e_steps, "depth": chain_depth, "launches_per_step": chain_launches,
                                  "what": "the reference's flow: operands uploaded once, a chain of ops on resident data (here `depth` rounds of "
                                          "NTT -> product with a resident plaintext -> INTT per limb), result downloaded once",
                                  "limb_ntts_per_step_per_gpu": 2 * chain_depth * ntts_per_step}},
@@ -765,7 +769,8 @@ def measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank, sh
             comm = hks.GroupComm(grp)
         else:
             comm = hks.LocalComm()
-        overlap = world > 1 and not os.environ.get("ALOHA_BENCH_KS_NO_OVERLAP")
+        # phase 2 under the all-gather: "own" = the digits this rank produced run first, without waiting
+        overlap = {"none": False, "own": "own", "chunks": "chunks"}[os.environ.get("ALOHA_BENCH_KS_OVERLAP", "own")] if world > 1 else False
         ks = hks.KeySwitch(eng, lay, comm, overlap=overlap)
 
         def limb_inputs(i, b=0):      # any rank can regenerate any limb's inputs
@@ -845,7 +850,7 @@ def measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank, sh
                "transfers": None if world == 1 else {
                    "backend": "NCCL inside libaloha_b200.so (aloha_group_*), communication stream per GPU",
                    "all_gather_bytes": lay.slots * N * 8 * batch, "broadcast_bytes": 2 * K * N * 8 * batch,
-                   "overlapped_with_phase2": overlap, "ms_compute_only": ms_compute,
+                   "overlap_mode": overlap or "none", "ms_compute_only": ms_compute,
                    "ms_exposed": ms / steps - ms_compute},
                "output_limbs_checked_against_oracle": int(flag[1].item()), "checked_against_oracle": all_ok,
                "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,

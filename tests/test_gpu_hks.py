@@ -167,7 +167,7 @@ def replay_case(world, n, L, K, dnum, overlap):
     return got, want, out.stdout
 
 
-@pytest.mark.parametrize("overlap", [False, True])
+@pytest.mark.parametrize("overlap", [False, "chunks"])
 def test_c_replay_tool_one_rank(overlap):
     """the C host program + aloha_group_* with a group of one (NCCL initialised, collectives degenerate)"""
     L = 6
@@ -185,7 +185,7 @@ def _ngpus():
         return 0
 
 
-@pytest.mark.parametrize("overlap", [False, True])
+@pytest.mark.parametrize("overlap", [False, "chunks", "own"])
 def test_c_replay_tool_two_ranks_nccl(overlap):
     if _ngpus() < 2:
         pytest.skip("needs two GPUs")
@@ -195,7 +195,7 @@ def test_c_replay_tool_two_ranks_nccl(overlap):
         assert (got[i][0] == want[0, i][0]).all() and (got[i][1] == want[0, i][1]).all(), i
 
 
-@pytest.mark.parametrize("overlap", [False, True])
+@pytest.mark.parametrize("overlap", [False, "chunks", "own"])
 def test_python_group_two_engines_nccl(overlap):
     """aloha_group_create_local from Python: two engines, the engine's own (non-torch) streams, chunked
     all-gather with per-source waits -- against the one-machine oracle run."""

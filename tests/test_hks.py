@@ -194,7 +194,7 @@ def _worker(rank, world, shape, overlap, port, qout):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap,port", [(False, 29541), (True, 29542)])
+@pytest.mark.parametrize("overlap,port", [(False, 29541), ("chunks", 29542), ("own", 29543)])
 def test_world2_gloo_equals_single_machine(overlap, port):
     shape = (256, 6, 2, 3)
     world = 2
