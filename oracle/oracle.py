@@ -38,12 +38,17 @@ def build(force: bool = False) -> str:
     path = os.path.join(_HERE, "libaloha_oracle_native.so") if native else _LIB_PATH
     src = [os.path.join(_HERE, f) for f in ("golden_model.cpp", "golden_model.h", "Makefile")]
     if force or not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in src):
-        try:
-            subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []) + (["native"] if native else []))
-        except Exception:
-            if not native:
-                raise
-            path = build_portable()
+        if not native:
+            subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []))
+        else:
+            # several ranks of one job may get here at once: each builds into its own file and renames it into
+            # place (atomic), so nobody ever loads a half-written library
+            tmp = f"libaloha_oracle_native.{os.getpid()}.tmp.so"
+            try:
+                subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "native", f"NATIVE_OUT={tmp}"])
+                os.replace(os.path.join(_HERE, tmp), path)
+            except Exception:
+                path = build_portable()
     return path
 
 
