@@ -143,6 +143,31 @@ def bind_to_gpu_numa_node(gpu: int):
     return None
 
 
+def run_guarded(fn, seconds, line, key, world):
+    """fn() on every rank; if it raises, or does not return within `seconds` on this rank, the rank leaves the job
+    cleanly: rank 0 (the one holding `line`) prints the line with line[key] = {"error": ...} first.  A rank that
+    raised cannot rejoin the others' collectives, so with several ranks it leaves at once and the rest follow
+    through their own watchdogs."""
+    def bail(reason):
+        if line is not None:
+            line[key] = {"error": reason}
+            print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os._exit(0)
+    timer = threading.Timer(seconds, bail, args=(f"did not finish within {seconds} s on this rank; skipped",))
+    timer.daemon = True
+    timer.start()
+    try:
+        return fn()
+    except Exception as e:                      # noqa: BLE001 -- reported in the line, not swallowed
+        timer.cancel()
+        if world > 1:
+            bail(f"{type(e).__name__}: {e}")
+        return {"error": f"{type(e).__name__}: {e}"}
+    finally:
+        timer.cancel()
+
+
 def workload_params():
     from aloha_b200 import params
     primes = params.synthetic_primes(LIMBS, 2 * N)
@@ -411,7 +436,6 @@ def run_gpu(args):
         if world == 1:
             extra["automorphism"] = measure_rotmac(torch, A, asm, eng_kwargs, primes, psis, stream, timed, POLYS)
             extra["tv_latency"] = measure_tv_latency(A)
-        extra["keyswitch"] = measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank)
 
     # end to end: host buffers in, host buffers out, every step
     # Host buffers -> SPM -> NTT -> host buffers, through the C-ABI only.  The batch is cut into
@@ -558,7 +582,16 @@ def run_gpu(args):
         if world == 1:
             line["cpu_baseline"] = {"value": cpu_all, "unit": "limb-NTTs/s", "cores": cores, "kind": "port",
                                     "sample": sample_all, "single_thread": cpu_one, "gpu_output_checked_against_oracle": ok}
-        print(json.dumps(line))
+    if not args.no_extra:
+        # The key-switch streams (config 5) come last and under a watchdog: they are the only part of this program
+        # with a data-path collective, and an auxiliary measurement must not take the headline line down with it.
+        eng.close()
+        ks = run_guarded(lambda: measure_keyswitch(torch, dist, A, {"device": local}, stream, timed, world, rank),
+                         400, line if rank == 0 else None, "keyswitch", world)
+        if rank == 0:
+            line["keyswitch"] = ks
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     if not ok:
@@ -810,12 +843,16 @@ def measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank, sh
             compute_only = [op for op in prog if op[0] == "run"]
             ks.execute(compute_only)
             ms_compute = timed(lambda: ks.execute(compute_only), steps) / steps
-        # per-phase device time of one key-switch (each phase timed alone, transfers excluded)
-        runs = [op for op in prog if op[0] == "run" and op[1]]
+        # per-phase device time of one key-switch (each phase timed alone, transfers excluded).  EVERY rank makes
+        # exactly three timed() calls -- timed() holds barriers and an all-reduce -- whatever it owns: a rank
+        # holding only special primes has nothing to run in phases 1 and 3, and under the overlap modes the
+        # number of phase-2 chunks differs from rank to rank.
+        run_ops = [op for op in prog if op[0] == "run"]
+        assert len(run_ops) >= 3
         phase_ms = []
-        for op in runs:
-            ks.execute([op])
-            phase_ms.append(timed(lambda op=op: ks.execute([op]), 10) / 10)
+        for part in (run_ops[:1], run_ops[1:-1], run_ops[-1:]):
+            ks.execute(part)
+            phase_ms.append(timed(lambda part=part: ks.execute(part), 10) / 10)
         # parity at full size: output limbs of this rank against the oracle
         ks.execute(prog)
         mine = [i for i in lay.owned() if i < L]

@@ -219,6 +219,32 @@ def test_world2_gloo_equals_single_machine(overlap, port):
     assert seen == set(range(L))
 
 
+@pytest.mark.parametrize("L,K,dnum", [(47, 1, 47), (40, 8, 5)])
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("overlap", [False, "own", "chunks"])
+def test_every_rank_issues_the_same_collectives(L, K, dnum, world, overlap):
+    """The config-5 shapes at 2 / 4 / 8 machines: whatever a rank owns (at 8 machines one of them holds nothing but
+    special primes), its op list carries the same transfers in the same order as every other rank's, at least
+    three run ops (phase 1, phase 2 chunk(s), phase 3), and a wait before anything that reads transferred rows."""
+    n = 256
+    primes = params.synthetic_primes(L + K, 2 * n)
+    prm = hks.Params(n, primes[K:], primes[:K], dnum)
+    seqs = []
+    for r in range(world):
+        lay = hks.Layout(prm, world, r, batch=2)
+        ks = hks.KeySwitch(hks.Recorder(), lay, type("C", (), {"world": world, "rank": r})(), overlap=overlap)
+        prog = ks.program(pow(3, 5, 2 * n))
+        seqs.append([op for op in prog if op[0] in ("all_gather", "broadcast")])
+        runs = [op for op in prog if op[0] == "run"]
+        assert len(runs) >= 3, (r, len(runs))
+        kinds = [op[0] for op in prog]
+        assert kinds[0] == "run" and kinds[1] == "all_gather" and kinds[-1] == "run" and kinds[-2] == "wait"
+        # every limb of every batch element is covered exactly once by phase 1 and by phase 3 over the ranks
+        assert len(runs[0][1]) == 2 * len([t for t in lay.owned() if t < L]) == len(runs[-1][1])
+    assert all(s == seqs[0] for s in seqs), "ranks disagree on the transfers"
+    assert len(seqs[0]) >= 2
+
+
 def test_layout_limits_and_counts():
     n = 65536
     q = list(range(40))
