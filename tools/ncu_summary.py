@@ -4,6 +4,8 @@ DESIGN.md cite:  profiles/<tag>_ncu_full_summary.json (selected metrics + stall 
 SASS lines by warp samples) and profiles/<tag>_traffic.json (DRAM bytes per launch pair).
 
 usage: tools/ncu_summary.py gpurun_out/r1_final_fwd.ncu-rep profiles/r1_ntt_fwd "<capture command>"
+       tools/ncu_summary.py <rep> <prefix> "<command>" --kernels      (any kernels: one entry per kernel name, the
+                                                                      longest launch; no NTT traffic file)
 """
 import csv
 import io
@@ -62,6 +64,15 @@ def main():
         top = sorted(blk["rows"], key=lambda r: -int(r[si]))[:8]
         k["hottest_sass_by_warp_samples"] = {"total_samples": total,
                                              "lines": [{"samples": int(r[si]), "sass": " ".join(r[so].split())} for r in top]}
+    if "--kernels" in sys.argv:
+        best = {}
+        for k in kernels:
+            name = k["Kernel Name"]["value"]
+            if name not in best or float(k["gpu__time_duration.sum"]["value"]) > float(best[name]["gpu__time_duration.sum"]["value"]):
+                best[name] = k
+        json.dump({"source": command, "kernels": list(best.values())}, open(prefix + "_ncu_full_summary.json", "w"), indent=1)
+        print(prefix + "_ncu_full_summary.json", len(best), "kernels")
+        return
     json.dump({"source": command, "kernels": kernels}, open(prefix + "_ncu_full_summary.json", "w"), indent=1)
     gb = lambda k, m: int(round(float(k[m]["value"]) * 1e9)) if k[m]["unit"] == "Gbyte" else int(float(k[m]["value"]))
     traffic = {"source": prefix + "_ncu_full_summary.json", "unit": "bytes per launch pair (one bench step: 2048 limb-NTTs, N=65536)"}
