@@ -82,7 +82,8 @@ class Params:
 class Layout:
     """SPM / KSK row map and limb ownership for one machine of `world`, `batch` key-switches side by side."""
 
-    def __init__(self, prm: Params, world: int = 1, rank: int = 0, batch: int = 1, kind: str = "rotate"):
+    def __init__(self, prm: Params, world: int = 1, rank: int = 0, batch: int = 1, kind: str = "rotate", base: int = 0):
+        """base: first SPM row of the layout (other data may live below it)"""
         assert kind in ("rotate", "relin")
         self.prm, self.world, self.rank, self.batch, self.kind = prm, world, rank, batch, kind
         L, K, rp = prm.L, prm.K, prm.rp
@@ -97,7 +98,7 @@ class Layout:
         for name in ("IN_size", "S_size", "ACC_size", "OUT_size"):
             if getattr(self, name) > 65536:
                 raise ValueError(f"region {name[:-5]} exceeds the 16-bit row offset of VLE/VSE; reduce L or N")
-        self.IN = 0
+        self.IN = base
         self.S = self.IN + batch * self.IN_size
         self.ACC = self.S + batch * self.S_size
         self.OUT = self.ACC + batch * self.ACC_size
@@ -513,14 +514,22 @@ class Rescale:
     the same instruction pattern as the key-switch's mod-down (keyswitch.mem insts 79-120) with P = q_last.
     Regions: IN = ct (2 L polys) , T (2 polys), OUT (2 (L-1) polys)."""
 
-    def __init__(self, machine, n: int, q: list[int], world: int = 1, rank: int = 0, comm=None, pc_base: int = 0):
+    def __init__(self, machine, n: int, q: list[int], world: int = 1, rank: int = 0, comm=None, pc_base: int = 0,
+                 in_row: int | None = None, base: int = 0, per_rank: int | None = None):
+        """in_row: the ciphertext is already in the SPM at this row (component c, limb i at (c L + i) polys) --
+        e.g. a key-switch's OUT region; T and OUT then start at `base`.  per_rank: limbs per machine when the
+        ownership is another stage's (Layout.per_rank) rather than ceil(L / world)."""
         self.machine, self.n, self.q, self.rp = machine, n, list(q), n // 128
         self.comm = comm or LocalComm()
         self.world, self.rank = world, rank
         L, rp = len(self.q), self.rp
         self.L = L
-        self.per_rank = _ceil_div(L, world)
-        self.IN, self.T, self.OUT = 0, 2 * L * rp, (2 * L + 2) * rp
+        self.per_rank = per_rank or _ceil_div(L, world)
+        if in_row is None:
+            self.IN, self.T = base, base + 2 * L * rp
+        else:
+            self.IN, self.T = in_row, base
+        self.OUT = self.T + 2 * rp
         self.spm_rows = self.OUT + 2 * (L - 1) * rp
         if 2 * L * rp > 65536:
             raise ValueError("region exceeds the 16-bit row offset of VLE/VSE")
@@ -564,8 +573,82 @@ class Rescale:
             m.run_vp(self.pc_t, self.IN, 0, self.T, 0, 0)
         self.comm.broadcast(m, self.T, 2 * self.rp, self.owner(self.L - 1), 1, 0)
         self.comm.wait(m, -2)
-        m.run_vp_multi([(pc, self.IN, self.T, self.OUT, 0, 0) for pc in self.pc_out.values()])
+        if self.pc_out:
+            m.run_vp_multi([(pc, self.IN, self.T, self.OUT, 0, 0) for pc in self.pc_out.values()])
 
     def read_output(self, i: int):
         return (self.machine.dma_mem_d2h(self.OUT + i * self.rp, self.n),
                 self.machine.dma_mem_d2h(self.OUT + (self.L - 1 + i) * self.rp, self.n))
+
+
+# ----------------------------------------------------------------------------------------------- multiply
+def tensor_stream(prm: Params, i: int) -> asm.Program:
+    """Limb i of the degree-2 product of two ciphertexts (evaluation form): src0 = X (a0 | a1 | b0 | b1, L limbs
+    each), rslt = the relinearise layout's IN (d0 | d1 | d2):
+        d0 = a0 b0,  d1 = a0 b1 + a1 b0,  d2 = a1 b1.
+    mul_plain.mem's VLE / VFQMUL.vv / VSE pattern with hom_add.mem's VFQADD.vv (B.3); the
+    operands of every vv instruction sit in different register banks."""
+    rp, L = prm.rp, prm.L
+    p = asm.Program().vsetvl(prm.n).vsetq(prm.q[i])
+    p.vle(0, asm.BASE_SRC0, i * rp).vle(2, asm.BASE_SRC0, (L + i) * rp)                 # a0, a1: even bank
+    p.vle(1, asm.BASE_SRC0, (2 * L + i) * rp).vle(3, asm.BASE_SRC0, (3 * L + i) * rp)   # b0, b1: odd bank
+    p.vfqmul(4, 0, 1).vse(4, asm.BASE_RSLT, i * rp)
+    p.vfqmul(5, 0, 3).vfqmul(8, 2, 1).vfqadd(10, 5, 8).vse(10, asm.BASE_RSLT, (L + i) * rp)
+    p.vfqmul(6, 2, 3).vse(6, asm.BASE_RSLT, (2 * L + i) * rp)
+    return p.brk()
+
+
+class Multiply:
+    """Ciphertext x ciphertext on one machine of a group: tensor product, relinearise (hybrid key-switch of d2
+    under the relinearisation key), rescale by the last prime -- three stages of per-limb streams over ONE
+    scratchpad image, the output of each stage read by the next where it lies:
+        X [4 L polys] | relinearise layout (IN = d0 d1 d2, S, ACC, OUT = c0 c1) | rescale T, OUT.
+    Limb ownership is the key-switch's (Layout.owner) for all three stages, so the only exchanges are the
+    key-switch's all-gather and broadcast and the rescale's broadcast of the dropped limb."""
+
+    def __init__(self, machine, prm: Params, world: int = 1, rank: int = 0, comm=None, pc_base: int = 0,
+                 overlap=False, rescale: bool = True):
+        L, rp = prm.L, prm.rp
+        self.machine, self.prm = machine, prm
+        self.X = 0
+        self.lay = Layout(prm, world, rank, 1, "relin", base=4 * L * rp)
+        self.ks = KeySwitch(machine, self.lay, comm, pc_base, overlap)
+        pc = self.ks.pc_end
+        self.pc_tensor = {}
+        for i in self.lay.owned():
+            if i < L:
+                words = tensor_stream(prm, i).words()
+                machine.load_isram(words, pc)
+                self.pc_tensor[i] = pc
+                pc += len(words)
+        self.rs = None
+        if rescale:
+            self.rs = Rescale(machine, prm.n, prm.q, world, rank, self.ks.comm, pc, in_row=self.lay.OUT,
+                              base=self.lay.spm_rows, per_rank=self.lay.per_rank)
+            pc = self.rs.pc_end
+        self.pc_end = pc
+
+    @staticmethod
+    def spm_rows(prm: Params, world: int = 1, rescale: bool = True) -> int:
+        end = Layout(prm, world, 0, 1, "relin", base=4 * prm.L * prm.rp).spm_rows
+        return end + (2 * prm.L * prm.rp if rescale else 0)
+
+    def load_input(self, i: int, a: tuple, b: tuple):
+        """limb i of the two ciphertexts: a = (a0_i, a1_i), b = (b0_i, b1_i)"""
+        L, rp = self.prm.L, self.prm.rp
+        for c, x in enumerate((*a, *b)):
+            self.machine.dma_mem_h2d(self.X + (c * L + i) * rp, x)
+
+    def load_ksk(self, t: int, data: np.ndarray):
+        self.ks.load_ksk(t, data)
+
+    def run(self):
+        lay = self.lay
+        self.machine.run_vp_multi([(pc, self.X, 0, lay.IN, 0, 0) for pc in self.pc_tensor.values()])
+        self.ks.run(1)
+        if self.rs is not None:
+            self.rs.run()
+
+    def read_output(self, i: int):
+        """limb i (rescale: i < L - 1) of the product ciphertext"""
+        return self.rs.read_output(i) if self.rs is not None else self.ks.read_output(i)
