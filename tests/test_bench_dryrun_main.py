@@ -149,6 +149,15 @@ def test_two_ranks_reach_the_end_together():
     assert "automorphism" not in line and "cpu_baseline" not in line           # one-GPU legs
 
 
+def test_eight_ranks_reach_the_end_together():
+    """the driver's largest scaling point: one rank owns nothing but special primes in the key-switch leg"""
+    outs = run(8, ["--gpus", "8", "--steps", "2", "--warmup", "3", "--polys", "8"], port=29583)
+    line = the_line(outs[0])
+    assert all(not [l for l in o.splitlines() if l.startswith("{")] for o in outs[1:])
+    assert line["n_gpus"] == 8 and len(line["per_rank"]["ms_timed_region"]) == 8
+    assert all("error" not in v and v["checked_against_oracle"] for v in line["keyswitch"].values())
+
+
 def test_reference_arm_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=600, env=dict(os.environ, ALOHA_ORACLE_NATIVE=""))
