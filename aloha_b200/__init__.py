@@ -85,6 +85,12 @@ def load_library(rebuild: bool = False) -> C.CDLL:
     if not os.path.exists(path):
         raise AlohaError(-8, "load_library", f"{path} is missing and cannot be built (no nvcc); "
                          "the engine has no CPU fallback")
+    _lib = bind_library(path)
+    return _lib
+
+
+def bind_library(path: str) -> C.CDLL:
+    """dlopen `path` and declare the C-ABI of include/aloha_b200.h on it; every symbol must be there."""
     L = C.CDLL(path)
     u64, u32, vp = C.c_uint64, C.c_uint32, C.c_void_p
     p64, p8 = C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)
@@ -141,7 +147,6 @@ def load_library(rebuild: bool = False) -> C.CDLL:
     for name, (res, args) in sig.items():
         fn = getattr(L, name)   # raises AttributeError if the library lacks a declared symbol
         fn.restype, fn.argtypes = res, args
-    _lib = L
     return L
 
 

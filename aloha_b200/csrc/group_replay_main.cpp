@@ -93,7 +93,8 @@ int main(int argc, char **argv) {
         for (size_t i = 0; i < nmod; ++i) cfgf >> q[i] >> psi[i];
         if (!cfgf) die("malformed " + base + ".cfg");
         cfg.device = dev0 + r;
-        check(aloha_create(&cfg, &eng[r]), eng[r], "aloha_create");
+        const int created = aloha_create(&cfg, &eng[r]);      // (eng[r] is read after the call: it carries the error text)
+        check(created, eng[r], "aloha_create");
         check(aloha_load_tf_rom(eng[r], q.data(), psi.data(), (uint32_t)nmod), eng[r], "aloha_load_tf_rom");
         const std::vector<uint8_t> rom = slurp(base + ".isram");
         check(aloha_load_isram(eng[r], rom.data(), (uint32_t)(rom.size() / 12), 0), eng[r], "aloha_load_isram");

@@ -1,5 +1,6 @@
-"""bench.py's whole GPU arm (`run_gpu`) walked on the CPU at a toy size, with one rank and with two (gloo): the
-oracle stands in for the engine, the CUDA stream / event / pinned-memory calls are stubbed, and everything else --
+"""bench.py's whole GPU arm (`run_gpu`) walked on the CPU at a toy size, with one rank, two and eight (gloo): the
+engine is the product's host code on the simulated device (tests/sim_engine.py), NCCL is gloo, torch's CUDA
+stream / event / pinned-memory calls are stubbed, and everything else --
 argument handling, warm-up policy, the end-to-end and op-chain legs, the automorphism and key-switch legs with
 their oracle checks, the assembly of the JSON line, the guarded tail -- is the program's own code.  It cannot say
 anything about speed; it says the program reaches its last line on every rank and prints ONE parseable line with
@@ -19,38 +20,16 @@ import ctypes, json, os, sys, time, types
 import numpy as np
 sys.path.insert(0, %(root)r)
 os.environ["ALOHA_BENCH_NO_SAMPLER"] = "1"
+os.environ["ALOHA_SIM_DEVICES"] = "8"
 os.environ.pop("ALOHA_ORACLE_NATIVE", None)
 import torch, torch.distributed as dist
 import aloha_b200 as A
 from oracle import oracle as O
 
-def view(ptr, nbytes):
-    return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint64)), shape=(nbytes // 8,))
-
-class FakeEngine:
-    make_args = staticmethod(A.Engine.make_args)
-    def __init__(self, vlmax_bits=A.VLMAX_BITS, spm_rows=A.SPM_ROWS, ksk_rows=A.KSK_ROWS, device=0, flags=0,
-                 moduli=A.REFERENCE_MODULI, pool_buffers=0, l2_chunk_bytes=0, isram_depth=0):
-        self.m = O.GoldenModel(vlmax_bits=vlmax_bits, spm_rows=spm_rows, ksk_rows=max(ksk_rows, 1), moduli=list(moduli) or [(O.Q0, O.PSI0)])
-        self.launches = 0
-    def set_stream(self, s): pass
-    def load_isram(self, w, pc): self.m.load_isram(w, pc)
-    def dma_ksk_h2d(self, row, data): self.m.dma_ksk_h2d(row, data)
-    def dma_mem_h2d(self, row, data):
-        self.m.dma_mem_h2d(row, view(*data).copy() if isinstance(data, tuple) else data)
-    def dma_mem_h2d_async(self, row, ptr, nbytes): self.m.dma_mem_h2d(row, view(ptr, nbytes).copy())
-    def dma_mem_d2h(self, row, nwords): return self.m.dma_mem_d2h(row, nwords)
-    def dma_mem_d2h_async(self, ptr, row, nbytes): view(ptr, nbytes)[:] = self.m.dma_mem_d2h(row, nbytes // 8)
-    def run_vp(self, *a): self.launches += 1; self.m.run_vp(*a)
-    def run_vp_batch(self, pc, args):
-        self.launches += 2
-        self.m.run_vp_batch(pc, [(a.src0, a.src1, a.rslt, a.ksk_ptr, a.step) for a in args] if not isinstance(args, list) else args)
-    def run_vp_multi(self, calls): self.launches += 1; self.m.run_vp_multi(calls)
-    def sync(self): pass
-    def stats(self):
-        return {k: self.launches for k in ("kernel_launches", "instructions", "plans_built", "plans_reused", "copies_elided",
-                                           "copies_emitted", "limb_ntts", "ops_fused")}
-    def close(self): self.m = None
+sys.path.insert(0, %(root)r + "/tests")
+import sim_engine
+_sim = sim_engine.simulated()
+_sim.__enter__()          # aloha_b200's own Engine class, bound to the engine's host code on the simulated device
 
 class FakeGroup:
     def __init__(self, e, r, w):
@@ -63,7 +42,7 @@ class FakeGroup:
     def wait(self, source=-1): pass
     def close(self): pass
 
-A.Engine, A.Group = FakeEngine, FakeGroup
+A.Group = FakeGroup
 
 # ---- CUDA stubs
 class Stream:

@@ -167,6 +167,11 @@ def replay_case(world, n, L, K, dnum, overlap):
     return got, want, out.stdout
 
 
+needs_a_real_device = pytest.mark.skipif(os.environ.get("ALOHA_TEST_DEVICE") == "sim",
+                                         reason="the C tool links the product library and NCCL: B200 only")
+
+
+@needs_a_real_device
 @pytest.mark.parametrize("overlap", [False, "chunks"])
 def test_c_replay_tool_one_rank(overlap):
     """the C host program + aloha_group_* with a group of one (NCCL initialised, collectives degenerate)"""

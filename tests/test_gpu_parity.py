@@ -566,8 +566,9 @@ def test_async_dma_pipeline_equals_blocking_dma():
     eng = A.Engine(vlmax_bits=n * 64, spm_rows=2 * B * per_poly, ksk_rows=0, moduli=list(zip(primes, psis)))
     eng.load_isram(asm.transform_stream(n, primes).words(), 0)
     rng = np.random.default_rng(4)
-    hin = torch.empty(B * L * n, dtype=torch.int64).pin_memory()
-    hout = torch.empty(B * L * n, dtype=torch.int64).pin_memory()
+    pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)     # (no driver on the simulated device)
+    hin = pin(torch.empty(B * L * n, dtype=torch.int64))
+    hout = pin(torch.empty(B * L * n, dtype=torch.int64))
     for rep in range(3):                      # reuse the same SPM rows and host buffers three times
         x = np.stack([rng.integers(0, primes[i % L], n, dtype=np.uint64) for i in range(B * L)])
         hin.numpy().view(np.uint64)[:] = x.reshape(-1)

@@ -1,0 +1,70 @@
+"""The batcher without a GPU: the engine's host sources built against a simulated device (tests/sim_engine.py,
+tests/native/sim/) and driven by the GPU suite's own test bodies.
+
+  * every `-m gpu` test that does not need NCCL or the C replay binary is run here, in a subprocess with
+    ALOHA_TEST_DEVICE=sim, against the oracle: the plans the batcher builds (store forwarding, copy-on-write,
+    fusion, levelling, plan cache, deferred queue, graphs, asynchronous DMA, the C host driver) compute what the
+    instruction streams say, and every launch satisfies the checks in sim_kernels.cpp (operands inside device
+    memory, no destination overlapping a permuted operand, no job reading what another job of the same launch
+    writes, row groups / tensor-map coordinates / tile plans / Shoup companions consistent with the job records);
+  * the simulated kernels do refuse what the real ones cannot take (so the first point is not vacuous);
+  * more fuzzing seeds than the GPU budget allows.
+None of this says anything about the sm_100a kernels: those are only checked on a B200."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import sim_engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_gpu_suite_on_the_simulated_device():
+    env = dict(os.environ, ALOHA_TEST_DEVICE="sim")
+    sim_engine.build()
+    workers = min(4, os.cpu_count() or 1)
+    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-q", "-m", "gpu", "-p", "no:cacheprovider"]
+    if workers > 1:
+        cmd += ["-n", str(workers)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1500, cwd=ROOT)
+    tail = out.stdout[-3000:] + out.stderr[-1000:]
+    assert out.returncode == 0, tail
+    summary = [l for l in out.stdout.splitlines() if " passed" in l][-1]
+    passed = int(summary.split(" passed")[0].split()[-1])
+    assert passed >= 150 and "failed" not in summary, summary
+
+
+@pytest.mark.parametrize("seed", range(1000, 1040))
+def test_more_fuzzing_than_the_gpu_budget_allows(seed):
+    import test_gpu_fuzz as F
+    with sim_engine.simulated() as A:
+        if seed % 3 == 2:
+            F.run_case(seed + 200000, strict=True, flags=A.F_STRICT | (A.F_DEFER if seed % 2 else 0))
+        else:
+            F.run_case(seed, strict=False, flags=[0, A.F_DEFER, A.F_NO_FUSE, A.F_GRAPHS][seed % 4])
+
+
+def test_simulated_kernels_refuse_what_the_real_ones_cannot_take():
+    """hand-made job tables straight into the simulated launchers: an automorphism in place, a job that reads
+    another job's output, an operand outside device memory -- each must fail the launch"""
+    code = r'''
+import ctypes as C, sys
+L = C.CDLL(sys.argv[1])
+for name in ("sim_test_vaut_in_place", "sim_test_cross_job_read", "sim_test_foreign_pointer", "sim_test_legal"):
+    fn = getattr(L, name); fn.restype = C.c_int
+    print(name, fn())
+'''
+    lib = sim_engine.build()
+    got = {}
+    for name in ("sim_test_vaut_in_place", "sim_test_cross_job_read", "sim_test_foreign_pointer", "sim_test_legal"):
+        # one process per case: a violation is sticky by design
+        out = subprocess.run([sys.executable, "-c", code.replace('("sim_test_vaut_in_place", "sim_test_cross_job_read", "sim_test_foreign_pointer", "sim_test_legal")', f'("{name}",)'), lib],
+                             capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr[-2000:]
+        got[name] = int(out.stdout.split()[-1])
+    assert got["sim_test_legal"] == 0
+    assert got["sim_test_vaut_in_place"] != 0 and got["sim_test_cross_job_read"] != 0 and got["sim_test_foreign_pointer"] != 0
