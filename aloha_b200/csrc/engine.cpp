@@ -726,6 +726,8 @@ size_t fuse_ops(std::vector<VecOp> &ops, const Loc *final_loc, const aloha *E) {
                 return -1;
             };
             src(o.a); src(o.b);
+            for (auto &t : o.ext) src(t.x);                               // operands of the ops fused above are reads too
+            for (auto &t : o.terms) { src(t.first); src(t.second); }
             prod_c[i] = src(o.c);
             writer[o.dst] = (int)i;
         }

@@ -36,3 +36,33 @@ def test_multiply_engine_equals_oracle(n, L, K, dnum):
         gx, gy = mul.read_output(i)
         assert (gx == x).all() and (gy == y).all(), i
     eng.close()
+
+
+def test_product_feeding_a_sum_of_products_and_a_base_extension():
+    """Regression (found by tests/test_sim_fuzz_idioms.py on the simulated device): a VFQMUL.vv product that is
+    the addend of a multiply-add chain AND a summand of a base-extension sum, and dies inside the plan.  The
+    sum-of-products pass recounted readers without the base extension's operands, took the product for a
+    single-use temporary, folded it into the chain -- and the base extension read a buffer nobody wrote."""
+    from aloha_b200 import asm
+    from oracle import oracle as O
+    n, rp, slots = 256, 2, 20
+    q, psi = O.Q0, pow(O.PSI0, 8192 // 256, O.Q0)
+    p1 = (asm.Program().vsetvl(n).vsetq(q)
+          .vle(19, 1, 18).vle(4, 2, 10).vfqadd(18, 19, 4).vfqmul(31, 18, 19)
+          .vle(13, 1, 0).vfqmul(28, 4, 13).vfqadd(31, 31, 28)                    # v31 = v18 v19 + v28
+          .vle(25, 1, 26).vcpy(12, 25).vfqmul(24, 12, imm=136326345680758277)
+          .vfqmul(13, 28, imm=238954420332171734).vfqadd(16, 24, 13)             # ... and v28 again, as a summand
+          .vfqmul(23, 4, imm=149856436604130345).vfqadd(20, 16, 23).vfqsub(9, 20, imm=565772908528373418)
+          .vntt(21, 9).vse(21, 0, 24).vse(31, 0, 26).brk())
+    p2 = asm.Program().vsetvl(n).vaut(28, 18, 1).vle(6, 1, 6).vaut(15, 6, 25).vaut(24, 18, 13).vfqmod(13, 15).vse(13, 2, 0).brk()
+    x = np.random.default_rng(18713).integers(0, q, slots * n, dtype=np.uint64)
+    images = []
+    for m in (O.GoldenModel(vlmax_bits=n * 64, spm_rows=slots * rp, ksk_rows=0, moduli=[(q, psi)]),
+              A.Engine(vlmax_bits=n * 64, spm_rows=slots * rp, ksk_rows=0, moduli=[(q, psi)], flags=A.F_DEFER, pool_buffers=34)):
+        m.dma_mem_h2d(0, x)
+        m.load_isram(p1.words(), 0)
+        m.load_isram(p2.words(), 64)
+        m.run_vp(0, 6, 10, 0, 0, 39)
+        m.run_vp(64, 10, 8, 8, 0, 48)           # queued behind the first call: one plan, in which v28, v24, v13 die
+        images.append(m.dma_mem_d2h(0, slots * n))
+    assert (images[0] == images[1]).all()
