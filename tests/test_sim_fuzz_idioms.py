@@ -20,6 +20,7 @@ from oracle import oracle as O
 N = 256
 RP = N // 128
 SLOTS = 20
+KSK_SLOTS = 4
 PRIMES = [O.Q0, O.Q1]
 PSIS = [pow(O.PSI0, 8192 // N, O.Q0), pow(O.PSI1, 8192 // N, O.Q1)]
 
@@ -46,8 +47,11 @@ class Gen:
         if c and self.rng.random() < 0.7:
             return self.rng.choice(c)
         r = self.reg(parity, avoid)
-        b = self.rng.randrange(3)
-        self.p.vle(r, b, self.slot(b))
+        if self.rng.random() < 0.15:
+            self.p.vle(r, asm.BASE_KSK, self.rng.randrange(KSK_SLOTS) * RP)      # key memory: read-only for the VP
+        else:
+            b = self.rng.randrange(3)
+            self.p.vle(r, b, self.slot(b))
         self.defined.add(r)
         return r
 
@@ -207,30 +211,46 @@ def run_case(A, seed: int):
     programs = [Gen(rng, defined, strict).program(rng.randrange(2, 7)) for _ in range(2 if pattern == "batch" else 3)]
     # (bases no larger than the first call's, so that the stream's row offsets stay inside the scratchpad)
     other_rows = tuple(rng.randrange(0, programs[0][1][b] // RP + 1) * RP for b in range(3)) + (0, programs[0][1][4])
-    machines = [O.GoldenModel(vlmax_bits=N * 64, spm_rows=SLOTS * RP, ksk_rows=0, moduli=list(zip(PRIMES, PSIS))),
-                A.Engine(vlmax_bits=N * 64, spm_rows=SLOTS * RP, ksk_rows=0, moduli=list(zip(PRIMES, PSIS)), flags=flags, pool_buffers=pool)]
+    machines = [O.GoldenModel(vlmax_bits=N * 64, spm_rows=SLOTS * RP, ksk_rows=KSK_SLOTS * RP, moduli=list(zip(PRIMES, PSIS))),
+                A.Engine(vlmax_bits=N * 64, spm_rows=SLOTS * RP, ksk_rows=KSK_SLOTS * RP, moduli=list(zip(PRIMES, PSIS)), flags=flags, pool_buffers=pool)]
+    ksk = data.integers(0, PRIMES[0], KSK_SLOTS * N, dtype=np.uint64)
+    # between the calls the host overwrites a few rows (registers aliasing them must keep their value) and reads some
+    host_rng = random.Random(seed ^ 0x5EED)
+    passes = 3 if seed % 2 else 1                         # later passes: cached plans replayed, on other data and entry states
+    host_writes = [(host_rng.randrange(SLOTS) * RP, data.integers(0, PRIMES[0], N, dtype=np.uint64)) for _ in range(2 * passes)]
     images = []
     for m in machines:
         m.dma_mem_h2d(0, spm0[: (SLOTS - 3) * N])
+        m.dma_ksk_h2d(0, ksk)
         pcs, pc = [], 0
         for prog, _ in programs:
             m.load_isram(prog.words(), pc)
             pcs.append(pc)
             pc += len(prog)
-        if pattern == "single":
-            for pc_, (_, csr) in zip(pcs, programs):
-                m.run_vp(pc_, *csr)
-        elif pattern == "multi":
-            m.run_vp(pcs[0], *programs[0][1])
-            m.run_vp_multi([(pcs[1], *programs[1][1]), (pcs[2], *programs[2][1])])
-        else:
-            m.run_vp_batch(pcs[0], [programs[0][1], other_rows])          # the same stream over two sets of rows
-            m.run_vp(pcs[1], *programs[1][1])
-        images.append((m.dma_mem_d2h(0, SLOTS * N), m.spm_written(0, SLOTS * N)))
+        seen = []
+        for ps in range(passes):
+            hw = iter(host_writes[2 * ps: 2 * ps + 2])
+            if pattern == "single":
+                for pc_, (_, csr) in zip(pcs, programs):
+                    m.run_vp(pc_, *csr)
+                    if pc_ == pcs[0]:
+                        m.dma_mem_h2d(*next(hw))
+            elif pattern == "multi":
+                m.run_vp(pcs[0], *programs[0][1])
+                m.dma_mem_h2d(*next(hw))
+                m.run_vp_multi([(pcs[1], *programs[1][1]), (pcs[2], *programs[2][1])])
+            else:
+                m.run_vp_batch(pcs[0], [programs[0][1], other_rows])      # the same stream over two sets of rows
+                m.dma_mem_h2d(*next(hw))
+                m.run_vp(pcs[1], *programs[1][1])
+            row, data_ = next(hw)
+            seen.append(m.dma_mem_d2h(row, N).copy())
+            m.dma_mem_h2d(row, data_)
+        images.append((np.concatenate([m.dma_mem_d2h(0, SLOTS * N)] + seen), m.spm_written(0, SLOTS * N)))
     (gd, gw), (ed, ew) = images
     assert (gw == ew).all(), f"seed {seed}: written-mask differs"
     bad = np.nonzero(gd != ed)[0]
-    assert bad.size == 0, f"seed {seed} ({pattern}, flags {flags:#x}, pool {pool}): {bad.size} words differ, first in slot {bad[0] // N}"
+    assert bad.size == 0, f"seed {seed} ({pattern}, flags {flags:#x}, pool {pool}, passes {passes}): {bad.size} words differ, first in slot {bad[0] // N}"
     return machines[1].stats()
 
 
