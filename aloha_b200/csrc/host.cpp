@@ -173,6 +173,12 @@ int aloha_host_run_op_async(aloha_host_t *H, uint32_t i, uint64_t *dump, uint8_t
     case OP_STORE: {
         const uint64_t a = kDramVpBase + op.dram_addr;
         if (a + bytes > H->dram.size()) return ALOHA_E_RANGE;
+        for (const PendingStore &p : H->pending)         // an earlier store to these DDR bytes still owes its dump,
+            if (p.dram_addr < a + bytes && a < p.dram_addr + p.bytes) {   // which is copied out of the DDR at the sync
+                rc = aloha_host_sync(H);
+                if (rc) return rc;
+                break;
+            }
         rc = read_back_async(H, op.spm_addr, bytes, (uint64_t *)(H->dram.data() + a));
         if (rc) return rc;
         H->pending.push_back(PendingStore{a, bytes, want_dump ? dump : nullptr});

@@ -1,10 +1,11 @@
-"""hks.Multiply (tensor product -> relinearise -> rescale over one scratchpad image) on the engine against the
-oracle machine, every output word.
+"""Tests added after the round's GPU minutes were spent: none of them has run on a B200 yet, all of them run on the
+simulated device in the CPU suite (tests/test_sim_engine.py).  The file sorts after every other GPU test on purpose.
 
-This file sorts after every other GPU test on purpose, and its test is xfail(strict=False): the composite was
-written after the round's GPU minutes were spent, so it has never run on a B200.  XPASS in the driver's log
-means it ran bit-exact; an xfail would be a finding about the engine, not about the streams (which
-tests/test_hks_multiply.py pins on the oracle machine)."""
+  * hks.Multiply (tensor product -> relinearise -> rescale over one scratchpad image) on the engine against the
+    oracle machine, every output word -- xfail(strict=False): XPASS in the driver's log means it ran bit-exact; an
+    xfail would be a finding about the engine, not about the streams (tests/test_hks_multiply.py pins those);
+  * regression tests of two host-side bugs the simulated device's fuzzers found (batcher: reader counts of fused
+    operands; host driver: two asynchronous stores to one DDR address)."""
 import numpy as np
 import pytest
 
@@ -66,3 +67,36 @@ def test_product_feeding_a_sum_of_products_and_a_base_extension():
         m.run_vp(64, 10, 8, 8, 0, 48)           # queued behind the first call: one plan, in which v28, v24, v13 die
         images.append(m.dma_mem_d2h(0, slots * n))
     assert (images[0] == images[1]).all()
+
+
+def test_two_stores_to_one_ddr_address_keep_their_own_dumps():
+    """Regression (found by tests/test_sim_fuzz_programs.py on the simulated device): in an asynchronous range the
+    dump of a store is copied out of the modelled DDR at the final sync; a second store to the same DDR bytes
+    inside the range used to overwrite them first, so both dumps showed the second ciphertext."""
+    import golden_util as G
+    from oracle import oracle as O
+    n = 8192
+    text = "\n".join(["10000400,00000000,003c0000", "10000300,00000000,00200000", "60000400,00000400,00000400",
+                      "10001100,00000000,002c0000", "20001100,00000000,00340000", "20001100,00000000,002c0000",
+                      "20000400,00000000,002c0000"])
+    ops = O.parse_program(text)
+    rng = np.random.default_rng(260)
+    dram = np.zeros(64 * 1024 * 1024 // 8, dtype=np.uint64)
+    eng = A.Engine()
+    model = O.GoldenModel()
+    for words, pc in G.microcode():
+        eng.load_isram(words, pc)
+        model.load_isram(words, pc)
+    host = A.HostDriver(eng, text, n)
+    for op in ops:
+        if op.kind == "load_cipher":
+            base = (O.DRAM_VP_BASE + op.dram_addr) // 8
+            dram[base:base + 4 * n] = rng.integers(0, O.Q0, 4 * n, dtype=np.uint64)
+            host.dram_write(O.DRAM_VP_BASE + op.dram_addr, dram[base:base + 4 * n])
+    want = [(i, d.copy(), w.copy()) for i, _, d, w in O.replay(model, ops, dram, {}, n)]
+    got = host.run_all_async()
+    for i, wd, ww in want:
+        (_, gd, gw), = got[i]
+        assert (np.asarray(gw, bool) == ww).all() and (gd[ww] == wd[ww]).all(), i
+    host.close()
+    eng.close()

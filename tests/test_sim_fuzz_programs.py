@@ -1,0 +1,113 @@
+"""Random host PROGRAMs (the testbench's op lists: load / encode / mul_plain / hom_add / rotate / store over the
+shipped microcode, top_noaxilite_tb.sv:249-298,596-638) through the C host driver on the simulated device
+(tests/sim_engine.py), blocking op by op and as one asynchronous range, under the PROGRAM-level flags; every dump
+and its written-mask against the oracle's replay of the same list.  The reference ships three such programs; this
+makes more, with operands that overlap, results written in place, and stores read back by later loads."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import golden_util as G
+import sim_engine
+from oracle import oracle as O
+
+N = 8192
+CT = 256                      # rows of a ciphertext (4 polynomials of 64 rows)
+STEPS = [2, 4, 8]
+
+
+def gen_program(rng: random.Random, n_ops: int):
+    lines, loads, enc = [], {}, {}
+    cts, pts = [], []
+    slot = lambda: rng.randrange(0, 40) * CT + (128 if rng.random() < 0.15 else 0)       # some half-ciphertext offsets
+    dram_slot = lambda: rng.randrange(0, 16) * 4 * N * 8
+    for i in range(n_ops):
+        kinds = ["load"] + (["encode"] if len(cts) else []) + (["mul", "add", "rotate", "store"] if cts and i > 1 else [])
+        kind = rng.choice(kinds) if cts else "load"
+        if kind == "mul" and not pts:
+            kind = "encode"
+        if kind == "load":
+            s, d = slot(), dram_slot()
+            lines.append(f"{0x10000000 | s:08x},{d >> 32:08x},{d & 0xFFFFFFFF:08x}")
+            loads[i] = d
+            cts.append(s)
+        elif kind == "encode":
+            s = slot()
+            lines.append(f"{0x30000000 | s:08x},00000000,00000000")
+            enc[i] = None
+            pts.append(s)
+        elif kind == "mul":
+            dst = rng.choice(cts + [slot()])
+            lines.append(f"{0x50000000 | dst:08x},{rng.choice(cts):08x},{rng.choice(pts):08x}")
+            cts.append(dst)
+        elif kind == "add":
+            dst = rng.choice(cts + [slot()])
+            lines.append(f"{0x60000000 | dst:08x},{rng.choice(cts):08x},{rng.choice(cts):08x}")
+            cts.append(dst)
+        elif kind == "rotate":
+            src = rng.choice(cts)
+            dst = rng.choice([c for c in cts if abs(c - src) >= CT] + [slot()])
+            if abs(dst - src) < CT:
+                dst = (src + CT * 2) % (40 * CT)
+            lines.append(f"{0x70000000 | dst:08x},{rng.choice(STEPS):08x},{src:08x}")
+            cts.append(dst)
+        else:
+            d = dram_slot()
+            lines.append(f"{0x20000000 | rng.choice(cts):08x},{d >> 32:08x},{d & 0xFFFFFFFF:08x}")
+    return lines, loads, enc
+
+
+def run_case(A, seed):
+    rng = random.Random(seed)
+    data = np.random.default_rng(seed)
+    lines, loads, enc = gen_program(rng, rng.randrange(4, 12))
+    text = "\n".join(lines)
+    ops = O.parse_program(text)
+    flags = rng.choice([0, A.F_DEFER, A.F_GRAPHS, A.F_DEFER | A.F_GRAPHS, A.F_NO_FUSE])
+    dram0 = np.zeros(64 * 1024 * 1024 // 8, dtype=np.uint64)
+    for d in set(loads.values()):
+        base = (O.DRAM_VP_BASE + d) // 8
+        dram0[base:base + 4 * N] = data.integers(0, O.Q0, 4 * N, dtype=np.uint64)
+    enc = {i: data.integers(0, O.Q0, 2 * N, dtype=np.uint64) for i in enc}
+    ksk = data.integers(0, O.Q0, 3 * 12 * N, dtype=np.uint64)                   # the keys of steps 2, 4, 8
+
+    model = O.GoldenModel()
+    for words, pc in G.microcode():
+        model.load_isram(words, pc)
+    model.dma_ksk_h2d(0, ksk)
+    dram = dram0.copy()
+    want = [(i, sub, d.copy(), w.copy()) for i, sub, d, w in O.replay(model, ops, dram, enc, N)]
+
+    for mode in ("blocking", "async"):
+        eng = A.Engine(flags=flags)
+        for words, pc in G.microcode():
+            eng.load_isram(words, pc)
+        eng.dma_ksk_h2d(0, ksk)
+        host = A.HostDriver(eng, text, N)
+        for i, e in enc.items():
+            host.set_encoder_output(i, e)
+        for d in set(loads.values()):
+            base = (O.DRAM_VP_BASE + d) // 8
+            host.dram_write(O.DRAM_VP_BASE + d, dram0[base:base + 4 * N])
+        per_op = [host.run_op(i) for i in range(len(ops))] if mode == "blocking" else host.run_all_async()
+        got = [(i, sub, d, w) for i, dumps in enumerate(per_op) for sub, d, w in dumps]
+        assert [(i, s) for i, s, _, _ in got] == [(i, s) for i, s, _, _ in want], (seed, mode)
+        for (i, sub, gd, gw), (_, _, wd, ww) in zip(got, want):
+            assert (np.asarray(gw, bool) == ww).all(), (seed, mode, hex(flags), i, sub, "written-mask")
+            assert (gd[ww] == wd[ww]).all(), (seed, mode, hex(flags), i, sub, text)
+        for i, op in enumerate(ops):
+            if op.kind == "store_cipher":
+                base = (O.DRAM_VP_BASE + op.dram_addr) // 8
+                assert (host.dram_read(O.DRAM_VP_BASE + op.dram_addr, 4 * N) == dram[base:base + 4 * N]).all(), (seed, mode, i)
+        host.close()
+        eng.close()
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_random_host_programs(block):
+    per = int(os.environ.get("ALOHA_PROGRAM_SEEDS", "3"))
+    with sim_engine.simulated() as A:
+        for seed in range(block * per, (block + 1) * per):
+            run_case(A, seed)
