@@ -80,7 +80,7 @@ def run_case(A, seed):
     dram = dram0.copy()
     want = [(i, sub, d.copy(), w.copy()) for i, sub, d, w in O.replay(model, ops, dram, enc, N)]
 
-    for mode in ("blocking", "async"):
+    for mode in ("blocking", "async", "mixed"):
         eng = A.Engine(flags=flags)
         for words, pc in G.microcode():
             eng.load_isram(words, pc)
@@ -91,7 +91,19 @@ def run_case(A, seed):
         for d in set(loads.values()):
             base = (O.DRAM_VP_BASE + d) // 8
             host.dram_write(O.DRAM_VP_BASE + d, dram0[base:base + 4 * N])
-        per_op = [host.run_op(i) for i in range(len(ops))] if mode == "blocking" else host.run_all_async()
+        if mode == "blocking":
+            per_op = [host.run_op(i) for i in range(len(ops))]
+        elif mode == "async":
+            per_op = host.run_all_async()
+        else:                                             # ranges of random length, some asynchronous, some op by op
+            per_op, i = [], 0
+            while i < len(ops):
+                cnt = min(len(ops) - i, rng.randrange(1, 5))
+                if rng.random() < 0.5:
+                    per_op += [[(s_, d_.copy(), w_.copy()) for s_, d_, w_ in dumps] for dumps in host.run_all_async(i, cnt)]
+                else:
+                    per_op += [host.run_op(j) for j in range(i, i + cnt)]
+                i += cnt
         got = [(i, sub, d, w) for i, dumps in enumerate(per_op) for sub, d, w in dumps]
         assert [(i, s) for i, s, _, _ in got] == [(i, s) for i, s, _, _ in want], (seed, mode)
         for (i, sub, gd, gw), (_, _, wd, ww) in zip(got, want):
