@@ -82,10 +82,10 @@ struct Check {
 };
 
 template <class Job, class Fn>
-cudaError_t run(const char *kernel, const Job *jobs, u32 njobs, unsigned launches, Fn fn) {
+cudaError_t run(cudaStream_t st, const char *kernel, const Job *jobs, u32 njobs, unsigned launches, Fn fn) {
     g_launches += launches;
     if (!njobs) return cudaErrorInvalidValue;                 // a zero-sized grid is a launch error on the device too
-    sim::enqueue([=]() {
+    sim::enqueue(st, [=]() {
         if (!sim::device_range(jobs, (size_t)njobs * sizeof(Job))) { sim::violation((std::string(kernel) + ": job table is not device memory").c_str()); return; }
         // every job is checked before any runs, and all of a launch's jobs read their operands before any writes
         // (jobs of one launch are unordered on the device: a job must not consume another job's output)
@@ -106,7 +106,12 @@ cudaError_t run(const char *kernel, const Job *jobs, u32 njobs, unsigned launche
                 for (auto &r : checks[i].reads)
                     if (Check::overlap(dst[j], len[j], r.first, r.second)) { sim::violation((std::string(kernel) + ": a job reads words another job of the same launch writes").c_str()); return; }
             }
-        for (u32 j = 0; j < njobs; ++j) std::memcpy(dst[j], out[j].data(), len[j] * 8);
+        sim::access(jobs, (size_t)njobs * sizeof(Job), false, kernel);
+        for (u32 j = 0; j < njobs; ++j) {
+            for (auto &r : checks[j].reads) sim::access(r.first, r.second * 8, false, kernel);
+            sim::access(dst[j], len[j] * 8, true, kernel);
+            std::memcpy(dst[j], out[j].data(), len[j] * 8);
+        }
     });
     return sim::status();
 }
@@ -176,23 +181,23 @@ void check_groups(const NttJob *jobs, const NttRowGroup *groups, u32 ngroups, u3
 
 }  // namespace
 
-cudaError_t launch_ntt_forward(const NttJob *jobs, u32 njobs, const NttRowGroup *groups, u32 ngroups, u32 logn, u32 form, cudaStream_t) {
+cudaError_t launch_ntt_forward(const NttJob *jobs, u32 njobs, const NttRowGroup *groups, u32 ngroups, u32 logn, u32 form, cudaStream_t st) {
     if (16 * ngroups > njobs || logn < 8 || logn > 16 || form > FORM_PM) return cudaErrorInvalidValue;
-    sim::enqueue([=]() { Check c; if (sim::device_range(jobs, (size_t)njobs * sizeof(NttJob))) check_groups(jobs, groups, ngroups, logn, false, nullptr, c); if (!c.ok) sim::violation(("ntt_forward: " + c.what).c_str()); });
+    sim::enqueue(st, [=]() { Check c; if (sim::device_range(jobs, (size_t)njobs * sizeof(NttJob))) check_groups(jobs, groups, ngroups, logn, false, nullptr, c); if (!c.ok) sim::violation(("ntt_forward: " + c.what).c_str()); });
     const unsigned launches = (logn > 8) + (ngroups != 0) + (njobs > 16 * ngroups);
-    return run("ntt_forward", jobs, njobs, launches, [=](const NttJob &j, Check &c, std::vector<u64> &o, u64 *&d) { transform(j, logn, form, false, c, o, d); });
+    return run(st, "ntt_forward", jobs, njobs, launches, [=](const NttJob &j, Check &c, std::vector<u64> &o, u64 *&d) { transform(j, logn, form, false, c, o, d); });
 }
-cudaError_t launch_ntt_inverse(const NttJob *jobs, u32 njobs, const NttRowGroup *groups, u32 ngroups, const TmaMaps *maps, u32 logn, u32 form, cudaStream_t) {
+cudaError_t launch_ntt_inverse(const NttJob *jobs, u32 njobs, const NttRowGroup *groups, u32 ngroups, const TmaMaps *maps, u32 logn, u32 form, cudaStream_t st) {
     if (16 * ngroups > njobs || (ngroups && !maps) || logn < 8 || logn > 16 || form > FORM_PM) return cudaErrorInvalidValue;
     const TmaMaps held = maps ? *maps : TmaMaps{};          // passed by value to the real kernel
-    sim::enqueue([=]() { Check c; if (sim::device_range(jobs, (size_t)njobs * sizeof(NttJob))) check_groups(jobs, groups, ngroups, logn, true, &held, c); if (!c.ok) sim::violation(("ntt_inverse: " + c.what).c_str()); });
+    sim::enqueue(st, [=]() { Check c; if (sim::device_range(jobs, (size_t)njobs * sizeof(NttJob))) check_groups(jobs, groups, ngroups, logn, true, &held, c); if (!c.ok) sim::violation(("ntt_inverse: " + c.what).c_str()); });
     const unsigned launches = (logn > 8) + (ngroups != 0) + (njobs > 16 * ngroups);
-    return run("ntt_inverse", jobs, njobs, launches, [=](const NttJob &j, Check &c, std::vector<u64> &o, u64 *&d) { transform(j, logn, form, true, c, o, d); });
+    return run(st, "ntt_inverse", jobs, njobs, launches, [=](const NttJob &j, Check &c, std::vector<u64> &o, u64 *&d) { transform(j, logn, form, true, c, o, d); });
 }
 
-cudaError_t launch_pease(const PeaseJob *jobs, u32 njobs, u32 logn, u32 stage, bool inverse, cudaStream_t) {
+cudaError_t launch_pease(const PeaseJob *jobs, u32 njobs, u32 logn, u32 stage, bool inverse, cudaStream_t st) {
     if (stage >= logn) return cudaErrorInvalidValue;
-    return run("pease", jobs, njobs, 1, [=](const PeaseJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
+    return run(st, "pease", jobs, njobs, 1, [=](const PeaseJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
         const u32 n = 1u << logn;
         c.in(j.src, n, "src"); c.dev(j.dst, n, "dst"); c.dev(j.tw, 2 * n, "twiddle table");
         c.apart(j.dst, j.src, n, "src");
@@ -204,10 +209,10 @@ cudaError_t launch_pease(const PeaseJob *jobs, u32 njobs, u32 logn, u32 stage, b
     });
 }
 
-cudaError_t launch_ew(u32 op, const EwJob *jobs, u32 njobs, u32 n, cudaStream_t) {
+cudaError_t launch_ew(u32 op, const EwJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
     const bool vv = op == 0x00 || op == 0x01 || op == 0x02;
     if (!(vv || op == 0x04 || op == 0x05 || op == 0x06 || op == 0x0a || op == 0x03)) return cudaErrorInvalidValue;
-    return run("ew", jobs, njobs, 1, [=](const EwJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
+    return run(st, "ew", jobs, njobs, 1, [=](const EwJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
         c.in(j.a, n, "a"); c.dev(j.dst, n, "dst");
         c.same_or_apart(j.dst, j.a, n, "a");
         if (vv) { c.in(j.b, n, "b"); c.same_or_apart(j.dst, j.b, n, "b"); }
@@ -218,8 +223,8 @@ cudaError_t launch_ew(u32 op, const EwJob *jobs, u32 njobs, u32 n, cudaStream_t)
     });
 }
 
-cudaError_t launch_copy(const CopyJob *jobs, u32 njobs, u32 n, cudaStream_t) {
-    return run("copy", jobs, njobs, 1, [=](const CopyJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
+cudaError_t launch_copy(const CopyJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
+    return run(st, "copy", jobs, njobs, 1, [=](const CopyJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
         c.in(j.src, n, "src"); c.dev(j.dst, n, "dst");
         c.same_or_apart(j.dst, j.src, n, "src");
         if (!c.ok) return;
@@ -240,8 +245,8 @@ void automorph(const u64 *x, u32 n, u64 k, u64 q, std::vector<u64> &o) {
 bool odd_and_inverse(u64 k, u64 kinv, u32 n) { return (k & 1) && ((k * kinv) & (n - 1)) == 1; }
 }  // namespace
 
-cudaError_t launch_vaut(const PermJob *jobs, u32 njobs, u32 n, cudaStream_t) {
-    return run("vaut", jobs, njobs, 1, [=](const PermJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
+cudaError_t launch_vaut(const PermJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
+    return run(st, "vaut", jobs, njobs, 1, [=](const PermJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
         c.in(j.src, n, "src"); c.dev(j.dst, n, "dst"); c.apart(j.dst, j.src, n, "src");
         if (!odd_and_inverse(j.k, j.kinv, n)) c.fail("kinv is not k^-1 mod n (or k is even)");
         if (!c.ok) return;
@@ -249,8 +254,8 @@ cudaError_t launch_vaut(const PermJob *jobs, u32 njobs, u32 n, cudaStream_t) {
         d = j.dst;
     });
 }
-cudaError_t launch_vaut_tiled(const AutJob *jobs, u32 njobs, u32 n, u32 max_tiles, cudaStream_t) {
-    return run("vaut_tiled", jobs, njobs, 1, [=](const AutJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
+cudaError_t launch_vaut_tiled(const AutJob *jobs, u32 njobs, u32 n, u32 max_tiles, cudaStream_t st) {
+    return run(st, "vaut_tiled", jobs, njobs, 1, [=](const AutJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
         c.in(j.src, n, "src"); c.dev(j.dst, n, "dst"); c.apart(j.dst, j.src, n, "src");
         const AutPlan want = make_aut_plan(n, j.k);
         if (std::memcmp(&want, &j.plan, sizeof want) != 0) c.fail("tile plan is not make_aut_plan(n, k)");
@@ -261,8 +266,8 @@ cudaError_t launch_vaut_tiled(const AutJob *jobs, u32 njobs, u32 n, u32 max_tile
         d = j.dst;
     });
 }
-cudaError_t launch_vroli(const PermJob *jobs, u32 njobs, u32 n, cudaStream_t) {
-    return run("vroli", jobs, njobs, 1, [=](const PermJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
+cudaError_t launch_vroli(const PermJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
+    return run(st, "vroli", jobs, njobs, 1, [=](const PermJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
         c.in(j.src, n, "src"); c.dev(j.dst, n, "dst"); c.apart(j.dst, j.src, n, "src");
         if (!c.ok) return;
         o.resize(n);
@@ -290,16 +295,16 @@ void autmac(const AutMacJob &j, u32 n, bool tiled, u32 max_tiles, Check &c, std:
     d = j.dst;
 }
 }  // namespace
-cudaError_t launch_autmac(const AutMacJob *jobs, u32 njobs, u32 n, cudaStream_t) {
-    return run("autmac", jobs, njobs, 1, [=](const AutMacJob &j, Check &c, std::vector<u64> &o, u64 *&d) { autmac(j, n, false, 0, c, o, d); });
+cudaError_t launch_autmac(const AutMacJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
+    return run(st, "autmac", jobs, njobs, 1, [=](const AutMacJob &j, Check &c, std::vector<u64> &o, u64 *&d) { autmac(j, n, false, 0, c, o, d); });
 }
-cudaError_t launch_autmac_tiled(const AutMacJob *jobs, u32 njobs, u32 n, u32 max_tiles, cudaStream_t) {
-    return run("autmac_tiled", jobs, njobs, 1, [=](const AutMacJob &j, Check &c, std::vector<u64> &o, u64 *&d) { autmac(j, n, true, max_tiles, c, o, d); });
+cudaError_t launch_autmac_tiled(const AutMacJob *jobs, u32 njobs, u32 n, u32 max_tiles, cudaStream_t st) {
+    return run(st, "autmac_tiled", jobs, njobs, 1, [=](const AutMacJob &j, Check &c, std::vector<u64> &o, u64 *&d) { autmac(j, n, true, max_tiles, c, o, d); });
 }
 
-cudaError_t launch_mac(const MacJob *jobs, u32 njobs, u32 terms, u32 n, cudaStream_t) {
+cudaError_t launch_mac(const MacJob *jobs, u32 njobs, u32 terms, u32 n, cudaStream_t st) {
     if (terms < 1 || terms > 4) return cudaErrorInvalidValue;
-    return run("mac", jobs, njobs, 1, [=](const MacJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
+    return run(st, "mac", jobs, njobs, 1, [=](const MacJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
         c.dev(j.dst, n, "dst");
         for (u32 t = 0; t < terms; ++t) { c.in(j.a[t], n, "a"); c.in(j.b[t], n, "b"); c.same_or_apart(j.dst, j.a[t], n, "a"); c.same_or_apart(j.dst, j.b[t], n, "b"); }
         if (!c.ok) return;
@@ -315,8 +320,8 @@ cudaError_t launch_mac(const MacJob *jobs, u32 njobs, u32 terms, u32 n, cudaStre
         d = j.dst;
     });
 }
-cudaError_t launch_muladd(const MulAddJob *jobs, u32 njobs, u32 n, cudaStream_t) {
-    return run("muladd", jobs, njobs, 1, [=](const MulAddJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
+cudaError_t launch_muladd(const MulAddJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
+    return run(st, "muladd", jobs, njobs, 1, [=](const MulAddJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
         c.in(j.a, n, "a"); c.in(j.b, n, "b"); c.in(j.c, n, "c"); c.dev(j.dst, n, "dst");
         c.same_or_apart(j.dst, j.a, n, "a"); c.same_or_apart(j.dst, j.b, n, "b"); c.same_or_apart(j.dst, j.c, n, "c");
         if (!c.ok) return;
@@ -325,8 +330,8 @@ cudaError_t launch_muladd(const MulAddJob *jobs, u32 njobs, u32 n, cudaStream_t)
         d = j.dst;
     });
 }
-cudaError_t launch_sop(const SopJob *jobs, u32 njobs, u32 n, cudaStream_t) {
-    return run("sop", jobs, njobs, 1, [=](const SopJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
+cudaError_t launch_sop(const SopJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
+    return run(st, "sop", jobs, njobs, 1, [=](const SopJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
         c.dev(j.dst, n, "dst");
         if (!j.terms) c.fail("no terms");
         if (((uintptr_t)j.pairs & 15) || !sim::device_range(j.pairs, (size_t)j.terms * 16)) { c.fail("pointer table is not 16-byte aligned device memory"); return; }
@@ -344,8 +349,8 @@ cudaError_t launch_sop(const SopJob *jobs, u32 njobs, u32 n, cudaStream_t) {
         d = j.dst;
     });
 }
-cudaError_t launch_bext(const BextJob *jobs, u32 njobs, u32 n, cudaStream_t) {
-    return run("bext", jobs, njobs, 1, [=](const BextJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
+cudaError_t launch_bext(const BextJob *jobs, u32 njobs, u32 n, cudaStream_t st) {
+    return run(st, "bext", jobs, njobs, 1, [=](const BextJob &j, Check &c, std::vector<u64> &o, u64 *&d) {
         c.dev(j.dst, n, "dst");
         if (!j.nterms) c.fail("no terms");
         if (!sim::device_range(j.terms, (size_t)j.nterms * sizeof(BextTerm))) { c.fail("term table is not device memory"); return; }
@@ -413,6 +418,23 @@ int sim_test_cross_job_read() {
     a.ew[1] = alb::EwJob{a.buf + 768, a.buf, a.buf + 512, 0, kQ, kIq};       // reads job 0's destination
     return alb::launch_ew(0x01, a.ew, 2, 256, nullptr);
 }
+static int two_streams(bool ordered, bool through_host) {
+    Arena a;
+    cudaStream_t s1, s2;
+    cudaEvent_t e;
+    cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    a.ew[0] = alb::EwJob{a.buf, a.buf + 256, a.buf + 512, 0, kQ, kIq};
+    cudaMemsetAsync(a.buf + 256, 0, 256 * 8, s1);                            // s1 writes an operand ...
+    if (ordered) { cudaEventRecord(e, s1); cudaStreamWaitEvent(s2, e, 0); }
+    if (through_host) cudaStreamSynchronize(s1);
+    alb::launch_ew(0x01, a.ew, 1, 256, s2);                                  // ... a kernel on s2 reads
+    return (int)cudaStreamSynchronize(s2);
+}
+int sim_test_race() { return two_streams(false, false); }
+int sim_test_race_ordered_by_event() { return two_streams(true, false); }
+int sim_test_race_ordered_by_host() { return two_streams(false, true); }
 int sim_test_foreign_pointer() {
     Arena a;
     static alb::u64 host_words[256];

@@ -6,7 +6,9 @@ tests/native/sim/) and driven by the GPU suite's own test bodies.
     fusion, levelling, plan cache, deferred queue, graphs, asynchronous DMA, the C host driver) compute what the
     instruction streams say, and every launch satisfies the checks in sim_kernels.cpp (operands inside device
     memory, no destination overlapping a permuted operand, no job reading what another job of the same launch
-    writes, row groups / tensor-map coordinates / tile plans / Shoup companions consistent with the job records);
+    writes, row groups / tensor-map coordinates / tile plans / Shoup companions consistent with the job records),
+    and no two operations on different streams touch the same device bytes without an event or a synchronisation
+    between them (vector clocks in sim_cuda.cpp: the asynchronous DMA channels against the engine's stream);
   * the simulated kernels do refuse what the real ones cannot take (so the first point is not vacuous);
   * more fuzzing seeds than the GPU budget allows.
 None of this says anything about the sm_100a kernels: those are only checked on a B200."""
@@ -49,22 +51,18 @@ def test_more_fuzzing_than_the_gpu_budget_allows(seed):
 
 
 def test_simulated_kernels_refuse_what_the_real_ones_cannot_take():
-    """hand-made job tables straight into the simulated launchers: an automorphism in place, a job that reads
-    another job's output, an operand outside device memory -- each must fail the launch"""
-    code = r'''
-import ctypes as C, sys
-L = C.CDLL(sys.argv[1])
-for name in ("sim_test_vaut_in_place", "sim_test_cross_job_read", "sim_test_foreign_pointer", "sim_test_legal"):
-    fn = getattr(L, name); fn.restype = C.c_int
-    print(name, fn())
-'''
+    """hand-made job tables and stream programs straight into the simulated runtime: an automorphism in place, a job
+    that reads another job's output, an operand outside device memory, a kernel reading what another stream wrote
+    with nothing ordering the two -- each must fail; the legal twins of those must not"""
+    code = "import ctypes as C, sys\nfn = getattr(C.CDLL(sys.argv[1]), sys.argv[2]); fn.restype = C.c_int; print(fn())"
     lib = sim_engine.build()
     got = {}
-    for name in ("sim_test_vaut_in_place", "sim_test_cross_job_read", "sim_test_foreign_pointer", "sim_test_legal"):
+    for name in ("sim_test_legal", "sim_test_vaut_in_place", "sim_test_cross_job_read", "sim_test_foreign_pointer",
+                 "sim_test_race", "sim_test_race_ordered_by_event", "sim_test_race_ordered_by_host"):
         # one process per case: a violation is sticky by design
-        out = subprocess.run([sys.executable, "-c", code.replace('("sim_test_vaut_in_place", "sim_test_cross_job_read", "sim_test_foreign_pointer", "sim_test_legal")', f'("{name}",)'), lib],
-                             capture_output=True, text=True, timeout=120)
+        out = subprocess.run([sys.executable, "-c", code, lib, name], capture_output=True, text=True, timeout=120)
         assert out.returncode == 0, out.stderr[-2000:]
         got[name] = int(out.stdout.split()[-1])
-    assert got["sim_test_legal"] == 0
+    assert got["sim_test_legal"] == 0 and got["sim_test_race_ordered_by_event"] == 0 and got["sim_test_race_ordered_by_host"] == 0
     assert got["sim_test_vaut_in_place"] != 0 and got["sim_test_cross_job_read"] != 0 and got["sim_test_foreign_pointer"] != 0
+    assert got["sim_test_race"] != 0
