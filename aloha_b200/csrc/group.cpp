@@ -15,6 +15,7 @@
 // it, and a process that already carries an NCCL (torch) shares that copy.
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -47,7 +48,9 @@ struct Nccl {
 Nccl &nccl() {
     static Nccl N;
     if (N.so || !N.error.empty()) return N;
-    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    // ALOHA_NCCL_LIB: a particular NCCL build (full path), tried before the system's
+    const char *env = std::getenv("ALOHA_NCCL_LIB");
+    const char *names[] = {env && *env ? env : "libnccl.so.2", "libnccl.so.2", "libnccl.so"};
     for (const char *n : names)
         if ((N.so = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
     if (!N.so) {

@@ -312,9 +312,12 @@ class KeySwitch:
         assert self.comm.world == lay.world and self.comm.rank == lay.rank
         prm = lay.prm
         self.overlap = ("chunks" if overlap is True else overlap) if lay.world > 1 else False
-        # digits whose source limbs all live on rank r can be consumed as soon as r's block has arrived;
-        # a digit that straddles two ranks waits for the later one
-        self.digit_rank = [max(lay.owner(j) for j in g) for g in prm.groups]
+        # a digit can be consumed once the blocks of all the ranks that hold some of its limbs have arrived: the chunked
+        # all-gather delivers the blocks in rank order, so a digit belongs to the chunk of the LAST such rank; it needs no
+        # wait at all only if every one of its limbs is this rank's own
+        self.digit_sources = [sorted({lay.owner(j) for j in g}) for g in prm.groups]
+        self.digit_rank = [src[-1] for src in self.digit_sources]
+        self.digit_local = [src == [lay.rank] for src in self.digit_sources]
         self.pc1, self.pc2, self.pc3 = {}, {}, {}
         pc = pc_base
 
@@ -331,26 +334,38 @@ class KeySwitch:
             if not self.overlap:
                 put(self.pc2, (t, None), phase2_stream(lay, t))
             else:
-                order = self.chunk_order()
+                order = [r for r in self.chunk_order() if self.chunk_digits(r)]      # (lockstep keeps empty chunks in the list)
                 for n_, r in enumerate(order):
                     put(self.pc2, (t, r), phase2_stream(lay, t, self.chunk_digits(r), first=n_ == 0, last=n_ == len(order) - 1))
         self.pc_end = pc
 
     def chunk_order(self) -> list[int]:
-        """Chunks of phase 2 in the order they run.  "chunks": one per source rank, own digits first, then the
-        order of arrival (lockstep: rank order for everyone).  "own": this rank's digits, then -1 = all the others."""
+        """Chunks of phase 2 in the order they run.  "chunks": one per source rank (the rank of a digit's last limb),
+        this rank's first, then the order of arrival (lockstep: rank order for everyone).  "own": the digits made of
+        this rank's limbs only (chunk = its rank), then -1 = all the others."""
         have = sorted({r for r in self.digit_rank})
         if self.overlap == "own":
-            mine = [r for r in have if r == self.lay.rank]
-            return mine + ([-1] if len(have) > len(mine) else [])
+            if self.lockstep:                   # every rank walks the same list, whether or not it holds a whole digit
+                return [self.lay.rank, -1]
+            mine = [self.lay.rank] if any(self.digit_local) else []
+            return mine + ([-1] if not all(self.digit_local) else [])
         if self.lockstep:
             return have
         return [r for r in have if r == self.lay.rank] + [r for r in have if r != self.lay.rank]
 
     def chunk_digits(self, r: int) -> list[int]:
-        if r == -1:
-            return [b for b in range(self.lay.prm.dnum) if self.digit_rank[b] != self.lay.rank]
-        return [b for b in range(self.lay.prm.dnum) if self.digit_rank[b] == r]
+        dnum = self.lay.prm.dnum
+        if self.overlap == "own":
+            return [b for b in range(dnum) if self.digit_local[b] == (r != -1)]
+        return [b for b in range(dnum) if self.digit_rank[b] == r]
+
+    def chunk_waits(self, r: int) -> list[int]:
+        """the transfers chunk r's digits must have seen arrive: ALOHA_GROUP_ALL for the unchunked all-gather, else the
+        source ranks of its digits' limbs (lockstep: this rank's own block included -- one list for every rank)"""
+        if self.overlap == "own":
+            return [-1] if r == -1 else []
+        need = sorted({s for b in self.chunk_digits(r) for s in self.digit_sources[b]})
+        return need if self.lockstep else [s for s in need if s != self.lay.rank]
 
     def load_ksk(self, t: int, data: np.ndarray):
         """data: KSK[t] = 2 dnum polynomials ([b][c] order) under modulus t; only the owner stores it."""
@@ -387,10 +402,10 @@ class KeySwitch:
                                 for b in range(B) for t in mine if want(t)]))
         else:
             for r in self.chunk_order():
-                if r != lay.rank or (self.lockstep and self.overlap == "chunks"):
-                    ops.append(("wait", r))
+                for source in self.chunk_waits(r):
+                    ops.append(("wait", source))
                 ops.append(("run", [(self.pc2[t, r], reg("S", b), reg("OUT", b), reg("ACC", b), lay.ksk_ptr(t), 0)
-                                    for b in range(B) for t in mine if want(t)]))
+                                    for b in range(B) for t in mine if want(t)] if self.chunk_digits(r) else []))
         for r in range(lay.world):
             ks = [t - prm.L for t in lay.owned(r) if t >= prm.L]
             if ks:

@@ -90,6 +90,35 @@ void access(const void *p, size_t bytes, bool write, const char *what) {
     if (g_log.size() > 200000) g_log.erase(g_log.begin(), g_log.begin() + 100000);     // (bounded: old entries first)
 }
 
+// One collective over several streams (sim_nccl.cpp): every rank's part is an operation of its own stream; a rank's
+// completion is ordered after the START of the ranks it receives from (root < 0: all of them; else: the root only).
+void collective(const std::vector<cudaStream_t> &streams, int root, const std::function<void(int rank)> &body) {
+    if (g_capture) die("collective inside a stream capture");
+    const int n = (int)streams.size();
+    std::vector<uint64_t> tick(n);
+    std::vector<Clock> started(n);
+    for (int r = 0; r < n; ++r) {
+        begin_op(streams[r]);
+        tick[r] = g_cur_tick;
+        std::lock_guard<std::mutex> lk(g_mu);
+        started[r] = g_stream_clock[(uintptr_t)streams[r]];
+        started[r][(uintptr_t)streams[r]] = tick[r] - 1;      // what had been queued before the collective itself
+    }
+    for (int r = 0; r < n; ++r) {
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            Clock &c = g_stream_clock[(uintptr_t)streams[r]];
+            for (int s = 0; s < n; ++s)
+                if (s != r && (root < 0 || s == root) && !(root >= 0 && r == root)) join(c, started[s]);
+        }
+        g_cur_stream = (uintptr_t)streams[r];
+        g_cur_tick = tick[r];
+        g_in_op = true;
+        body(r);
+        g_in_op = false;
+    }
+}
+
 void enqueue(cudaStream_t st, std::function<void()> fn) {
     if (g_capture) { g_capture->nodes.push_back(std::move(fn)); return; }
     begin_op(st);
@@ -122,6 +151,12 @@ static CUresult encode_tiled(CUtensorMap *map, CUtensorMapDataType, cuuint32_t r
 }  // namespace sim
 
 using namespace sim;
+
+// a new test starts from a clean slate (tests/sim_engine.py simulated())
+extern "C" void sim_reset_violation() {
+    std::lock_guard<std::mutex> lk(sim::g_mu);
+    sim::g_violation.clear();
+}
 
 const char *cudaGetErrorString(cudaError_t e) {
     switch (e) {

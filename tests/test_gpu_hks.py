@@ -18,6 +18,9 @@ import test_hks as T
 pytestmark = pytest.mark.gpu
 
 
+SIMULATED = os.environ.get("ALOHA_TEST_DEVICE") == "sim"       # tests/conftest.py: the engine's host code on a simulated device
+
+
 def engine_for(lay, prm, psi, device=0, **kw):
     return A.Engine(vlmax_bits=prm.n * 64, spm_rows=lay.spm_rows, ksk_rows=max(lay.ksk_rows, 1), device=device,
                     moduli=[(m, psi[m]) for m in prm.moduli], pool_buffers=kw.pop("pool_buffers", 512),
@@ -159,19 +162,17 @@ def replay_case(world, n, L, K, dnum, overlap):
     d = tempfile.mkdtemp(prefix="aloha_replay_")
     cfg = {"vlmax_bits": n * 64, "moduli": [(m, psi[m]) for m in prm.moduli], "pool_buffers": 256, "isram_depth": 65536}
     hks.write_replay_case(d, switches, cfg, loads, dumps, k)
-    tool = os.path.join(os.path.dirname(A.__file__), "aloha_group_replay")
-    out = subprocess.run([tool, d, str(world)], capture_output=True, text=True, timeout=300)
+    tool, env = os.path.join(os.path.dirname(A.__file__), "aloha_group_replay"), None
+    if SIMULATED:                    # the same C program linked against the engine's host code on the simulated device
+        import sim_engine
+        tool, env = sim_engine.REPLAY, dict(os.environ, ALOHA_NCCL_LIB=sim_engine.NCCL, ALOHA_SIM_DEVICES="8")
+    out = subprocess.run([tool, d, str(world)], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stderr + out.stdout
     got = {i: tuple(np.fromfile(os.path.join(d, f"out_{c}_{i}.u64"), dtype=np.uint64) for c in (0, 1)) for i in range(L)}
     want = T.run_machine(prm, psi, ct, ksk, k, "rotate")
     return got, want, out.stdout
 
 
-needs_a_real_device = pytest.mark.skipif(os.environ.get("ALOHA_TEST_DEVICE") == "sim",
-                                         reason="the C tool links the product library and NCCL: B200 only")
-
-
-@needs_a_real_device
 @pytest.mark.parametrize("overlap", [False, "chunks"])
 def test_c_replay_tool_one_rank(overlap):
     """the C host program + aloha_group_* with a group of one (NCCL initialised, collectives degenerate)"""
@@ -183,6 +184,8 @@ def test_c_replay_tool_one_rank(overlap):
 
 
 def _ngpus():
+    if SIMULATED:
+        return int(os.environ.get("ALOHA_SIM_DEVICES", "1"))
     try:
         import torch
         return torch.cuda.device_count()
@@ -200,32 +203,41 @@ def test_c_replay_tool_two_ranks_nccl(overlap):
         assert (got[i][0] == want[0, i][0]).all() and (got[i][1] == want[0, i][1]).all(), i
 
 
-@pytest.mark.parametrize("overlap", [False, "chunks", "own"])
-def test_python_group_two_engines_nccl(overlap):
-    """aloha_group_create_local from Python: two engines, the engine's own (non-torch) streams, chunked
-    all-gather with per-source waits -- against the one-machine oracle run."""
-    if _ngpus() < 2:
-        pytest.skip("needs two GPUs")
-    n, L, K, dnum, world = 2048, 6, 2, 3, 2
+def local_group_case(world, n, L, K, dnum, overlap, batch=2):
+    """aloha_group_create_local from Python: `world` engines in one process, the engine's own (non-torch) streams,
+    against the one-machine oracle run; twice, the second time on cached plans."""
     prm, psi, ct, ksk = T.make_problem(n, L, K, dnum, "rotate")
     k = pow(3, 9, 2 * n)
-    want = T.run_machine(prm, psi, ct, ksk, k, "rotate", batch=2)
+    want = T.run_machine(prm, psi, ct, ksk, k, "rotate", batch=batch)
     engines, switches = [], []
     for r in range(world):
-        lay = hks.Layout(prm, world, r, batch=2)
+        lay = hks.Layout(prm, world, r, batch=batch)
         engines.append(engine_for(lay, prm, psi, device=r))
     grp = A.Group.local(engines)
     for r in range(world):
-        lay = hks.Layout(prm, world, r, batch=2)
+        lay = hks.Layout(prm, world, r, batch=batch)
         ks = hks.KeySwitch(engines[r], lay, type("C", (), {"world": world, "rank": r})(), overlap=overlap, lockstep=True)
         fill(ks, lay, prm, ct, ksk)
         switches.append(ks)
     for _ in range(2):
         hks.run_local_group(switches, grp, k)
+    seen = set()
     for r, ks in enumerate(switches):
-        for b in range(2):
+        for b in range(batch):
             for i in ks.lay.owned():
                 if i < L:
                     gx, gy = ks.read_output(i, b)
                     assert (gx == want[b, i][0]).all() and (gy == want[b, i][1]).all(), (r, b, i)
+                    seen.add((b, i))
+    assert len(seen) == batch * L
     grp.close()
+    for e in engines:
+        e.close()
+
+
+@pytest.mark.parametrize("overlap", [False, "chunks", "own"])
+def test_python_group_two_engines_nccl(overlap):
+    """chunked all-gather with per-source waits, and the two other overlap modes, on two GPUs of one process"""
+    if _ngpus() < 2:
+        pytest.skip("needs two GPUs")
+    local_group_case(2, 2048, 6, 2, 3, overlap)

@@ -66,3 +66,37 @@ def test_simulated_kernels_refuse_what_the_real_ones_cannot_take():
     assert got["sim_test_legal"] == 0 and got["sim_test_race_ordered_by_event"] == 0 and got["sim_test_race_ordered_by_host"] == 0
     assert got["sim_test_vaut_in_place"] != 0 and got["sim_test_cross_job_read"] != 0 and got["sim_test_foreign_pointer"] != 0
     assert got["sim_test_race"] != 0
+
+
+@pytest.mark.parametrize("overlap", [False, "chunks", "own"])
+@pytest.mark.parametrize("world,L,K,dnum", [(8, 40, 8, 5), (8, 47, 1, 47), (4, 40, 8, 5), (3, 7, 2, 3)])
+def test_limb_sharded_key_switch_on_simulated_devices(world, L, K, dnum, overlap):
+    """group.cpp at the bench's two key-switch shapes over 8 and 4 devices (at 8, one rank owns nothing but special
+    primes) and over a world size that divides nothing: every output word against the one-machine oracle run, with the
+    simulated runtime checking that the engines' streams and the communication streams are ordered by events wherever
+    they touch the same rows.  NCCL is tests/native/sim/sim_nccl.cpp (one process, copies between the devices)."""
+    import test_gpu_hks as H
+    with sim_engine.simulated() as A:
+        H.A = A
+        try:
+            H.local_group_case(world, 256, L, K, dnum, overlap, batch=2)
+        finally:
+            import aloha_b200
+            H.A = aloha_b200
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_c_host_program_on_simulated_devices(world):
+    """aloha_group_replay (the C program of INTEGRATION.md, which sees only include/aloha_b200.h) linked against the
+    simulated library: config 5 without Python at 4 and 8 ranks"""
+    import test_gpu_hks as H
+    saved = H.SIMULATED
+    H.SIMULATED = True
+    try:
+        L = 13
+        got, want, log = H.replay_case(world, 256, L, 3, 5, "chunks")
+        for i in range(L):
+            assert (got[i][0] == want[0, i][0]).all() and (got[i][1] == want[0, i][1]).all(), i
+        assert f"{world} rank(s)" in log
+    finally:
+        H.SIMULATED = saved
