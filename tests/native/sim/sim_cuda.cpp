@@ -27,7 +27,7 @@ static std::mutex g_mu;
 static std::map<const uint8_t *, size_t> g_allocs;           // device allocations: base -> bytes
 static thread_local SimGraph *g_capture = nullptr;
 static thread_local cudaError_t g_last = cudaSuccess;
-static int g_device = 0;
+static thread_local int g_device = 0;
 static std::string g_violation;
 
 [[noreturn]] void die(const char *what) {

@@ -100,3 +100,58 @@ def test_c_host_program_on_simulated_devices(world):
         assert f"{world} rank(s)" in log
     finally:
         H.SIMULATED = saved
+
+
+def rank_per_thread_case(A, world, n, L, K, dnum, overlap, batch, passes=3):
+    """What bench.py's key-switch leg does with one process per GPU, here with one THREAD per simulated device:
+    aloha_group_create from a shared id, every rank walking its OWN op list (no lockstep), nobody waiting for a
+    block it does not need.  -> {(batch element, limb): (out_0, out_1)} collected from the ranks that own the limbs."""
+    import threading
+    import test_gpu_hks as H
+    import test_hks as T
+    from aloha_b200 import hks
+    prm, psi, ct, ksk = T.make_problem(n, L, K, dnum, "rotate")
+    k = pow(3, 9, 2 * n)
+    want = T.run_machine(prm, psi, ct, ksk, k, "rotate", batch=batch)
+    uid = A.Group.unique_id()
+    got, errors = {}, []
+
+    def rank_main(r):
+        try:
+            lay = hks.Layout(prm, world, r, batch=batch)
+            eng = A.Engine(vlmax_bits=n * 64, spm_rows=lay.spm_rows, ksk_rows=max(lay.ksk_rows, 1), device=r,
+                           moduli=[(m, psi[m]) for m in prm.moduli], pool_buffers=512, isram_depth=65536)
+            grp = A.Group.create(eng, uid, r, world)
+            ks = hks.KeySwitch(eng, lay, hks.GroupComm(grp), overlap=overlap)
+            H.fill(ks, lay, prm, ct, ksk)
+            for _ in range(passes):
+                ks.run(k)
+            eng.sync()
+            for b in range(batch):
+                for i in lay.owned():
+                    if i < L:
+                        got[b, i] = ks.read_output(i, b)
+            grp.close()
+            eng.close()
+        except BaseException as e:              # noqa: BLE001 -- reported by the caller
+            errors.append((r, repr(e)))
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    assert not any(t.is_alive() for t in threads), "a rank is stuck in a collective"
+    assert sorted(got) == sorted(want)
+    for key, (x, y) in want.items():
+        assert (got[key][0] == x).all() and (got[key][1] == y).all(), key
+
+
+@pytest.mark.parametrize("overlap", [False, "chunks", "own"])
+@pytest.mark.parametrize("world,L,K,dnum,batch", [(8, 40, 8, 5, 1), (8, 47, 1, 47, 1), (8, 40, 8, 5, 2), (4, 40, 8, 5, 1), (2, 40, 8, 5, 1), (5, 9, 2, 4, 2)])
+def test_one_rank_per_thread_like_one_process_per_gpu(world, L, K, dnum, batch, overlap):
+    """bench.py's multi-GPU key-switch path (aloha_group_create + each rank's own op list) at its two shapes over
+    2 / 4 / 8 simulated devices, and an awkward world size, under the stream-race check: this is the code the 8-GPU
+    run of the scaling bench executes, which no B200 box has run yet."""
+    with sim_engine.simulated() as A:
+        rank_per_thread_case(A, world, 256, L, K, dnum, overlap, batch)
