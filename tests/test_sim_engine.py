@@ -155,3 +155,49 @@ def test_one_rank_per_thread_like_one_process_per_gpu(world, L, K, dnum, batch, 
     run of the scaling bench executes, which no B200 box has run yet."""
     with sim_engine.simulated() as A:
         rank_per_thread_case(A, world, 256, L, K, dnum, overlap, batch)
+
+
+@pytest.mark.parametrize("world,overlap", [(2, False), (3, "own"), (4, "chunks")])
+def test_multiply_chain_one_rank_per_thread(world, overlap):
+    """tensor product -> relinearise -> rescale, limb-sharded over simulated devices with aloha_group_* transfers"""
+    import threading
+    import test_hks_multiply as M
+    from aloha_b200 import hks
+    n, L, K, dnum = 256, 7, 2, 3
+    prm, psi, a, b, ksk = M.problem(n, L, K, dnum)
+    want = M.run_multiply(prm, psi, a, b, ksk)
+    with sim_engine.simulated() as A:
+        uid = A.Group.unique_id()
+        got, errors = {}, []
+
+        def rank_main(r):
+            try:
+                lay = hks.Layout(prm, world, r, 1, "relin")
+                eng = A.Engine(vlmax_bits=n * 64, spm_rows=hks.Multiply.spm_rows(prm, world), ksk_rows=max(lay.ksk_rows, 1), device=r,
+                               moduli=[(m, psi[m]) for m in prm.moduli], pool_buffers=256, isram_depth=65536)
+                grp = A.Group.create(eng, uid, r, world)
+                mul = hks.Multiply(eng, prm, world, r, hks.GroupComm(grp), overlap=overlap)
+                for i in mul.lay.owned():
+                    if i < L:
+                        mul.load_input(i, (a[0][i], a[1][i]), (b[0][i], b[1][i]))
+                for t in mul.lay.owned():
+                    mul.load_ksk(t, np.stack([ksk[t][d][c] for d in range(prm.dnum) for c in (0, 1)]))
+                for _ in range(2):
+                    mul.run()
+                eng.sync()
+                for i in mul.lay.owned():
+                    if i < L - 1:
+                        got[i] = mul.read_output(i)
+                grp.close()
+                eng.close()
+            except BaseException as e:          # noqa: BLE001
+                errors.append((r, repr(e)))
+        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=300)
+        assert not errors, errors
+        assert sorted(got) == sorted(want)
+        for i, (x, y) in want.items():
+            assert (got[i][0] == x).all() and (got[i][1] == y).all(), i
