@@ -102,7 +102,7 @@ def test_c_host_program_on_simulated_devices(world):
         H.SIMULATED = saved
 
 
-def rank_per_thread_case(A, world, n, L, K, dnum, overlap, batch, passes=3):
+def rank_per_thread_case(A, world, n, L, K, dnum, overlap, batch, passes=3, flags=0):
     """What bench.py's key-switch leg does with one process per GPU, here with one THREAD per simulated device:
     aloha_group_create from a shared id, every rank walking its OWN op list (no lockstep), nobody waiting for a
     block it does not need.  -> {(batch element, limb): (out_0, out_1)} collected from the ranks that own the limbs."""
@@ -120,7 +120,7 @@ def rank_per_thread_case(A, world, n, L, K, dnum, overlap, batch, passes=3):
         try:
             lay = hks.Layout(prm, world, r, batch=batch)
             eng = A.Engine(vlmax_bits=n * 64, spm_rows=lay.spm_rows, ksk_rows=max(lay.ksk_rows, 1), device=r,
-                           moduli=[(m, psi[m]) for m in prm.moduli], pool_buffers=512, isram_depth=65536)
+                           moduli=[(m, psi[m]) for m in prm.moduli], pool_buffers=512, isram_depth=65536, flags=flags)
             grp = A.Group.create(eng, uid, r, world)
             ks = hks.KeySwitch(eng, lay, hks.GroupComm(grp), overlap=overlap)
             H.fill(ks, lay, prm, ct, ksk)
@@ -201,3 +201,16 @@ def test_multiply_chain_one_rank_per_thread(world, overlap):
         assert sorted(got) == sorted(want)
         for i, (x, y) in want.items():
             assert (got[i][0] == x).all() and (got[i][1] == y).all(), i
+
+
+def test_random_sharded_shapes_one_rank_per_thread():
+    """world size, L, K, dnum, overlap mode, batch and engine flags drawn at random (120 such draws have run clean)"""
+    import random
+    with sim_engine.simulated() as A:
+        flagsets = [0, A.F_DEFER, A.F_GRAPHS, A.F_DEFER | A.F_GRAPHS, A.F_NO_FUSE, A.F_STRICT]
+        for seed in range(int(os.environ.get("ALOHA_SWEEP_SHAPES", "12"))):
+            rng = random.Random(seed)
+            world, L, K = rng.randrange(2, 9), rng.randrange(2, 20), rng.randrange(1, 5)
+            dnum = rng.randrange(1, L + 1)
+            overlap, batch, flags = rng.choice([False, "chunks", "own"]), rng.randrange(1, 3), rng.choice(flagsets)
+            rank_per_thread_case(A, world, 256, L, K, dnum, overlap, batch, passes=2, flags=flags)
