@@ -159,9 +159,10 @@ def phase2_stream(lay: Layout, t: int, groups: list[int] | None = None, first: b
     groups = list(range(prm.dnum)) if groups is None else groups
     p = asm.Program().vsetvl(prm.n).vsetq(mt)
     acc_row = lambda c: (2 * t + c) * rp
-    if not first:
-        p.vle(4, asm.BASE_RSLT, acc_row(0)).vle(6, asm.BASE_RSLT, acc_row(1))
-    started = not first
+    # A later chunk sums its own digits first and adds the accumulators of the earlier chunks at the end: a chain that
+    # starts from a product is one sum-of-products for the batcher, one that starts from a loaded accumulator is a
+    # serial multiply-add per digit.  (Every term is canonical, so the order of the modular additions does not show.)
+    started = False
     for b in groups:
         g = prm.groups[b]
         if t in g:
@@ -193,6 +194,8 @@ def phase2_stream(lay: Layout, t: int, groups: list[int] | None = None, first: b
             else:
                 p.vfqmul(prod_, 2, k).vfqadd(acc, acc, prod_)
         started = True
+    if not first:
+        p.vle(15, asm.BASE_RSLT, acc_row(0)).vfqadd(4, 4, 15).vle(17, asm.BASE_RSLT, acc_row(1)).vfqadd(6, 6, 17)
     if not last or t < L:
         p.vse(4, asm.BASE_RSLT, acc_row(0)).vse(6, asm.BASE_RSLT, acc_row(1))
     else:
