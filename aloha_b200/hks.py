@@ -194,14 +194,18 @@ def phase2_stream(lay: Layout, t: int, groups: list[int] | None = None, first: b
             else:
                 p.vfqmul(prod_, 2, k).vfqadd(acc, acc, prod_)
         started = True
+    acc0, acc1 = 4, 6
     if not first:
-        p.vle(15, asm.BASE_RSLT, acc_row(0)).vfqadd(4, 4, 15).vle(17, asm.BASE_RSLT, acc_row(1)).vfqadd(6, 6, 17)
+        # (the sum lands in the register that held the earlier accumulator: were that register left aliasing the
+        #  accumulator's rows, the store below would have to copy it out of the way first)
+        p.vle(15, asm.BASE_RSLT, acc_row(0)).vfqadd(15, 15, 4).vle(17, asm.BASE_RSLT, acc_row(1)).vfqadd(17, 17, 6)
+        acc0, acc1 = 15, 17
     if not last or t < L:
-        p.vse(4, asm.BASE_RSLT, acc_row(0)).vse(6, asm.BASE_RSLT, acc_row(1))
+        p.vse(acc0, asm.BASE_RSLT, acc_row(0)).vse(acc1, asm.BASE_RSLT, acc_row(1))
     else:
         k = t - L
         half = prm.half % mt                                          # keyswitch.mem insts 79-82
-        for c, (acc, tmp, out) in enumerate(((4, 8, 10), (6, 9, 11))):
+        for c, (acc, tmp, out) in enumerate(((acc0, 8, 10), (acc1, 9, 11))):
             p.vintt(tmp, acc).vfqadd(out, tmp, imm=half)
             if K > 1:
                 p.vfqmul(12 + c, out, imm=prm.phat_inv[k])

@@ -12,6 +12,7 @@
 // which on in-domain inputs is what the fast kernels store, and on other inputs is what ALOHA_F_STRICT stores.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -84,6 +85,8 @@ struct Check {
 template <class Job, class Fn>
 cudaError_t run(cudaStream_t st, const char *kernel, const Job *jobs, u32 njobs, unsigned launches, Fn fn) {
     g_launches += launches;
+    static const bool trace = std::getenv("ALOHA_SIM_TRACE") != nullptr;     // one line per launch, for reading schedules
+    if (trace) std::fprintf(stderr, "sim launch %s jobs %u stream %p\n", kernel, njobs, (void *)st);
     if (!njobs) return cudaErrorInvalidValue;                 // a zero-sized grid is a launch error on the device too
     sim::enqueue(st, [=]() {
         if (!sim::device_range(jobs, (size_t)njobs * sizeof(Job))) { sim::violation((std::string(kernel) + ": job table is not device memory").c_str()); return; }
