@@ -243,6 +243,22 @@ def phase3_stream(lay: Layout, i: int) -> asm.Program:
     return p.brk()
 
 
+SCRATCH_REGS = tuple(range(0, 14)) + (15, 17)      # every register the phase streams write
+
+
+def retire_stream(prm: Params) -> asm.Program:
+    """Last call of every batch of phase streams: reload the scratch registers from key memory.  A VLE is an alias for
+    the batcher (no kernel), and it ends the lifetime of whatever the LAST phase stream of the batch left in those
+    registers -- architecturally visible values the batcher would otherwise have to materialise, which keeps that
+    stream's multiply / add / base-extension chains from fusing and trails a dozen one-job launches behind every
+    batch.  (Key memory, because the VP never writes it: aliases of scratchpad rows would have to be copied out of
+    the way by the next store to those rows.)"""
+    p = asm.Program().vsetvl(prm.n)
+    for r in SCRATCH_REGS:
+        p.vle(r, asm.BASE_KSK, 0)
+    return p.brk()
+
+
 # ---------------------------------------------------------------------------------------------- exchange
 class LocalComm:
     """world = 1: no exchange."""
@@ -334,6 +350,8 @@ class KeySwitch:
             machine.load_isram(words, pc)
             table[key] = pc
             pc += len(words)
+        self.pc_tail = {}
+        put(self.pc_tail, 0, retire_stream(prm))
         for t in lay.owned():
             if t < prm.L:
                 put(self.pc1, t, phase1_stream(lay, t))
@@ -421,7 +439,8 @@ class KeySwitch:
         src1 = "S" if lay.kind == "rotate" else "IN"
         ops.append(("run", [(self.pc3[i], reg("ACC", b), reg(src1, b), reg("OUT", b), 0, 0)
                             for b in range(B) for i in mine if i < prm.L and want(i)]))
-        return ops
+        tail = (self.pc_tail[0], 0, 0, 0, 0, 0)
+        return [("run", op[1] + [tail]) if op[0] == "run" and op[1] else op for op in ops]
 
     def execute(self, ops):
         m, comm = self.machine, self.comm
@@ -537,13 +556,14 @@ class Rescale:
     Regions: IN = ct (2 L polys) , T (2 polys), OUT (2 (L-1) polys)."""
 
     def __init__(self, machine, n: int, q: list[int], world: int = 1, rank: int = 0, comm=None, pc_base: int = 0,
-                 in_row: int | None = None, base: int = 0, per_rank: int | None = None):
+                 in_row: int | None = None, base: int = 0, per_rank: int | None = None, tail: tuple | None = None):
         """in_row: the ciphertext is already in the SPM at this row (component c, limb i at (c L + i) polys) --
         e.g. a key-switch's OUT region; T and OUT then start at `base`.  per_rank: limbs per machine when the
         ownership is another stage's (Layout.per_rank) rather than ceil(L / world)."""
         self.machine, self.n, self.q, self.rp = machine, n, list(q), n // 128
         self.comm = comm or LocalComm()
         self.world, self.rank = world, rank
+        self.tail = [tail] if tail else []       # a retire_stream call to close each batch with (needs key memory)
         L, rp = len(self.q), self.rp
         self.L = L
         self.per_rank = per_rank or _ceil_div(L, world)
@@ -592,11 +612,11 @@ class Rescale:
     def run(self):
         m = self.machine
         if self.pc_t is not None:
-            m.run_vp(self.pc_t, self.IN, 0, self.T, 0, 0)
+            m.run_vp_multi([(self.pc_t, self.IN, 0, self.T, 0, 0)] + self.tail)
         self.comm.broadcast(m, self.T, 2 * self.rp, self.owner(self.L - 1), 1, 0)
         self.comm.wait(m, -2)
         if self.pc_out:
-            m.run_vp_multi([(pc, self.IN, self.T, self.OUT, 0, 0) for pc in self.pc_out.values()])
+            m.run_vp_multi([(pc, self.IN, self.T, self.OUT, 0, 0) for pc in self.pc_out.values()] + self.tail)
 
     def read_output(self, i: int):
         return (self.machine.dma_mem_d2h(self.OUT + i * self.rp, self.n),
@@ -635,6 +655,7 @@ class Multiply:
         self.X = 0
         self.lay = Layout(prm, world, rank, 1, "relin", base=4 * L * rp)
         self.ks = KeySwitch(machine, self.lay, comm, pc_base, overlap)
+        self.tail = (self.ks.pc_tail[0], 0, 0, 0, 0, 0)
         pc = self.ks.pc_end
         self.pc_tensor = {}
         for i in self.lay.owned():
@@ -646,7 +667,7 @@ class Multiply:
         self.rs = None
         if rescale:
             self.rs = Rescale(machine, prm.n, prm.q, world, rank, self.ks.comm, pc, in_row=self.lay.OUT,
-                              base=self.lay.spm_rows, per_rank=self.lay.per_rank)
+                              base=self.lay.spm_rows, per_rank=self.lay.per_rank, tail=self.tail)
             pc = self.rs.pc_end
         self.pc_end = pc
 
@@ -666,7 +687,8 @@ class Multiply:
 
     def run(self):
         lay = self.lay
-        self.machine.run_vp_multi([(pc, self.X, 0, lay.IN, 0, 0) for pc in self.pc_tensor.values()])
+        if self.pc_tensor:
+            self.machine.run_vp_multi([(pc, self.X, 0, lay.IN, 0, 0) for pc in self.pc_tensor.values()] + [self.tail])
         self.ks.run(1)
         if self.rs is not None:
             self.rs.run()

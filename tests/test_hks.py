@@ -240,7 +240,9 @@ def test_every_rank_issues_the_same_collectives(L, K, dnum, world, overlap):
         kinds = [op[0] for op in prog]
         assert kinds[0] == "run" and kinds[1] == "all_gather" and kinds[-1] == "run" and kinds[-2] == "wait"
         # every limb of every batch element is covered exactly once by phase 1 and by phase 3 over the ranks
-        assert len(runs[0][1]) == 2 * len([t for t in lay.owned() if t < L]) == len(runs[-1][1])
+        # (+ 1: the retire stream that closes every non-empty batch; a rank without ciphertext limbs has empty batches)
+        limbs = 2 * len([t for t in lay.owned() if t < L])
+        assert len(runs[0][1]) == len(runs[-1][1]) == (limbs + 1 if limbs else 0)
     assert all(s == seqs[0] for s in seqs), "ranks disagree on the transfers"
     assert len(seqs[0]) >= 2
 
