@@ -1057,13 +1057,18 @@ void mark_written(aloha *E, u64 word_off, u64 nwords) {
     std::memset(E->written.data() + b0, 1, b1 - b0);
 }
 
-void commit(aloha *E, const Plan &plan) {
+void commit(aloha *E, Plan &plan) {
     E->vl = plan.vl; E->q = plan.q; E->iq = plan.iq; E->mod_idx = plan.mod_idx;
     // registers the plan never defined keep their location (an aliased register moved by a
     // copy-on-write is recorded as read + moved, hence its exit location is the plan's too)
     for (int r = 0; r < 32; ++r)
         if (((plan.killed_mask | plan.live_in_mask) >> r) & 1) E->loc[r] = plan.loc[r];
-    for (auto &w : plan.written) mark_written(E, w.first, w.second);
+    // the flags are never cleared, so a replayed plan has nothing left to mark (a 2048-polynomial step would
+    // otherwise memset 16 MiB of flags on the host every time it is replayed)
+    if (!plan.written_marked) {
+        for (auto &w : plan.written) mark_written(E, w.first, w.second);
+        plan.written_marked = true;
+    }
     E->stats.instructions += plan.instructions;
     E->stats.limb_ntts += plan.limb_ntts;
     E->stats.copies_elided += plan.elided;
@@ -1175,11 +1180,17 @@ int run_batch(aloha *E, const uint32_t *pcs, bool same_pc, uint32_t count, const
     } else {
         ++E->stats.plans_reused;
     }
-    if (!E->pending_down.empty())
-        for (auto &w : hit->written) {
-            int rc = wait_for_downloads(E, E->stream, w.first, w.second);
-            if (rc) return rc;
-        }
+    if (!E->pending_down.empty()) {
+        // one completion query per pending download, not one per (stored range, download) pair
+        int rc = wait_for_downloads(E, E->stream, 0, 0);        // (empty range: only retires the finished ones)
+        if (rc) return rc;
+        for (auto &p : E->pending_down)
+            for (auto &w : hit->written)
+                if (p.off < w.first + w.second && w.first < p.off + p.n) {
+                    CU(cudaStreamWaitEvent(E->stream, p.done, 0));
+                    break;
+                }
+    }
     int rc = execute_plan(E, *hit);
     if (rc) return rc;
     commit(E, *hit);

@@ -85,6 +85,7 @@ struct Plan {
     int mod_idx = -1;
     Loc loc[32];
     std::vector<std::pair<u64, u64>> written;   // SPM word ranges stored to
+    bool written_marked = false;                // the machine's written-flags already carry them (flags are only ever set)
     // entry conditions under which this plan may be replayed (everything else about the entry
     // state is irrelevant to it): registers it reads before writing must sit where they sat when it
     // was built; registers it overwrites may hold anything; the rest must not live in a pool buffer
