@@ -459,20 +459,18 @@ class HostDriver:
         if self._dump_pool is None or self._dump_pool[0].shape[0] < count:
             self._dump_pool = (self._pinned(count * w).reshape(count, w), self._pinned(count * w).reshape(count, w),
                                np.empty((count, w), np.uint8), np.empty((count, w), np.uint8), (C.c_int * count)())
+            d, s_, wr_, swr_, _ = self._dump_pool
+            # the per-op views handed back below, made once: the arrays are reused call after call
+            self._dump_views = [((0, s_[j], swr_[j].view(bool)), (None, d[j], wr_[j].view(bool))) for j in range(count)]
+            self._dump_ptrs = (_p64(d), _p8(wr_), _p64(s_), _p8(swr_))
         dumps, subs, wr, swr, has_sub = self._dump_pool
-        rc = self.L.aloha_host_run_range_async(self.h, first, count, _p64(dumps), _p8(wr), _p64(subs), _p8(swr), has_sub)
+        rc = self.L.aloha_host_run_range_async(self.h, first, count, *self._dump_ptrs, has_sub)
         if not rc:
             rc = self.L.aloha_host_sync(self.h)
         if rc:
             raise AlohaError(rc, "host_run_range_async", self.L.aloha_last_error(self.eng.h).decode())
-        out = []
-        for j in range(count):
-            ops = []
-            if has_sub[j]:
-                ops.append((0, subs[j], swr[j].view(bool)))
-            ops.append((None, dumps[j], wr[j].view(bool)))
-            out.append(ops)
-        return out
+        views = self._dump_views
+        return [list(views[j]) if has_sub[j] else [views[j][1]] for j in range(count)]
 
     @staticmethod
     def write_dump_text(path: str, data: np.ndarray, written: np.ndarray):

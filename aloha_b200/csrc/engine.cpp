@@ -1095,18 +1095,23 @@ int order_after(aloha *E, cudaStream_t waiter, cudaStream_t signaller) {
 }
 
 // Work about to be queued on `st` writes SPM words [off, off+n): it must not overtake a pending
-// asynchronous download of overlapping rows.
+// asynchronous download of overlapping rows.  Waiting on an event that has already completed costs nothing on the
+// device, so finished downloads are not looked for here (a completion query per pending download per call is a
+// microsecond each, quadratic over a program of dumped ops): aloha_sync retires them all, and a list that has grown
+// long without a sync is pruned once.
 int wait_for_downloads(aloha *E, cudaStream_t st, u64 off, u64 n) {
-    for (size_t i = 0; i < E->pending_down.size();) {
-        auto &p = E->pending_down[i];
-        if (cudaEventQuery(p.done) == cudaSuccess) {
-            put_event(E, p.done);
-            E->pending_down.erase(E->pending_down.begin() + i);
-            continue;
+    if (E->pending_down.size() >= 256) {
+        for (size_t i = 0; i < E->pending_down.size();) {
+            if (cudaEventQuery(E->pending_down[i].done) == cudaSuccess) {
+                put_event(E, E->pending_down[i].done);
+                E->pending_down.erase(E->pending_down.begin() + i);
+            } else {
+                ++i;
+            }
         }
-        if (p.off < off + n && off < p.off + p.n) CU(cudaStreamWaitEvent(st, p.done, 0));
-        ++i;
     }
+    for (auto &p : E->pending_down)
+        if (p.off < off + n && off < p.off + p.n) CU(cudaStreamWaitEvent(st, p.done, 0));
     return ALOHA_OK;
 }
 
@@ -1181,8 +1186,7 @@ int run_batch(aloha *E, const uint32_t *pcs, bool same_pc, uint32_t count, const
         ++E->stats.plans_reused;
     }
     if (!E->pending_down.empty()) {
-        // one completion query per pending download, not one per (stored range, download) pair
-        int rc = wait_for_downloads(E, E->stream, 0, 0);        // (empty range: only retires the finished ones)
+        int rc = wait_for_downloads(E, E->stream, 0, 0);        // (empty range: only prunes an overgrown list)
         if (rc) return rc;
         for (auto &p : E->pending_down)
             for (auto &w : hit->written)
@@ -1467,9 +1471,18 @@ int aloha_spm_written(aloha_t *E, uint32_t row, uint64_t nwords, uint8_t *out) {
     const u64 off = (u64)row * kLanes;
     if (off + nwords > E->spm_words) return fail(E, ALOHA_E_RANGE, "range beyond SPM");
     // one flag per 64-byte beat (8 words); `off` is row-aligned, hence beat-aligned
-    u64 i = 0;
-    for (; i + 8 <= nwords; i += 8) std::memset(out + i, E->written[(off + i) / 8], 8);
-    for (; i < nwords; ++i) out[i] = E->written[(off + i) / 8];
+    const uint8_t *flags = E->written.data() + off / 8;
+    const u64 beats = (nwords + 7) / 8;
+    // the flags are 0 or 1 and come in long runs (a dump is typically all written, or written up to some polynomial):
+    // one memchr + one memset per run
+    for (u64 b = 0; b < beats;) {
+        const uint8_t v = flags[b];
+        const void *e = std::memchr(flags + b, v ? 0 : 1, beats - b);
+        const u64 end = e ? (u64)((const uint8_t *)e - flags) : beats;
+        const u64 first = 8 * b, last = std::min<u64>(8 * end, nwords);
+        std::memset(out + first, v, last - first);
+        b = end;
+    }
     return ALOHA_OK;
 }
 
