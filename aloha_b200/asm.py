@@ -104,6 +104,10 @@ def rotate_mac_stream(n: int, moduli: list[int]) -> Program:
         p.vle(1, BASE_SRC1, l * rp).vfqmul(4, 2, 1)     # v4 = v2 * p
         p.vle(3, BASE_SRC1, (L + l) * rp).vfqadd(6, 4, 3)   # v6 = v4 + acc
         p.vse(6, BASE_RSLT, l * rp)
+    # Retire the last limb's temporaries: what v2 and v4 hold at BREAK is architecturally visible, so the batcher
+    # would have to materialise them -- three separate kernels for that limb instead of the fused one.  Reloading
+    # them from the row just stored is an alias (no kernel), and the next call redefines both before it stores there.
+    p.vle(2, BASE_RSLT, (L - 1) * rp).vle(4, BASE_RSLT, (L - 1) * rp)
     return p.brk()
 
 
