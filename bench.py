@@ -331,17 +331,21 @@ def run_gpu(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        h0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        host_ms = 1e3 * (time.perf_counter() - h0)      # what the host needed to enqueue the region (it does not wait in fn)
         e1.record(stream)
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        ms = torch.tensor([e0.elapsed_time(e1), host_ms], device="cuda")
+        timed.last_host_ms = [host_ms]
         if world > 1:
             allms = [torch.zeros_like(ms) for _ in range(world)]
             dist.all_gather(allms, ms)
-            timed.last_per_rank = [float(t.item()) for t in allms]
+            timed.last_per_rank = [float(t[0].item()) for t in allms]
+            timed.last_host_ms = [float(t[1].item()) for t in allms]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return float(ms[0].item())
 
     step = lambda: eng.run_vp_batch(0, calls)
     # Warm-up: at least W (>= 3) steps, and enough of them to keep every GPU busy for ~0.4 s -- with
@@ -370,6 +374,8 @@ def run_gpu(args):
         ms = timed(step, args.steps)
     s1 = eng.stats()
     per_rank_ms = getattr(timed, "last_per_rank", None)
+    host_enqueue_ms = list(timed.last_host_ms)          # of the headline's timed region: a rank whose host time approaches
+                                                        # its device time is enqueue-bound, not GPU-bound
     launches = s1["kernel_launches"] - s0["kernel_launches"]
     ntts_per_step = LIMBS * POLYS
     value = world * ntts_per_step * args.steps / (ms / 1e3)
@@ -576,8 +582,9 @@ def run_gpu(args):
         }
         if burst:
             line["burst"] = burst
+        line["host_enqueue_ms"] = host_enqueue_ms        # per rank, for the headline's timed region (ms_per_step * steps on the device)
         if world > 1:
-            line["per_rank"] = {"ms_timed_region": per_rank_ms, "cpu_affinity_of_rank0": numa}
+            line["per_rank"] = {"ms_timed_region": per_rank_ms, "host_enqueue_ms": host_enqueue_ms, "cpu_affinity_of_rank0": numa}
         line.update(extra)
         if world == 1:
             line["cpu_baseline"] = {"value": cpu_all, "unit": "limb-NTTs/s", "cores": cores, "kind": "port",
