@@ -1098,9 +1098,9 @@ int order_after(aloha *E, cudaStream_t waiter, cudaStream_t signaller) {
 // asynchronous download of overlapping rows.  Waiting on an event that has already completed costs nothing on the
 // device, so finished downloads are not looked for here (a completion query per pending download per call is a
 // microsecond each, quadratic over a program of dumped ops): aloha_sync retires them all, and a list that has grown
-// long without a sync is pruned once.
+// long (64) without a sync is pruned once.
 int wait_for_downloads(aloha *E, cudaStream_t st, u64 off, u64 n) {
-    if (E->pending_down.size() >= 256) {
+    if (E->pending_down.size() >= 64) {
         for (size_t i = 0; i < E->pending_down.size();) {
             if (cudaEventQuery(E->pending_down[i].done) == cudaSuccess) {
                 put_event(E, E->pending_down[i].done);
