@@ -227,25 +227,44 @@ def run_case(A, seed: int):
             m.load_isram(prog.words(), pc)
             pcs.append(pc)
             pc += len(prog)
-        seen = []
+        seen, keep = [], []
+        asynchronous = hasattr(m, "dma_mem_h2d_async") and seed % 4 < 2     # the DMA channels beside the VP (engine only)
+
+        def host_write(row, words):
+            if asynchronous:
+                buf = np.ascontiguousarray(words)
+                keep.append(buf)                          # stays valid until the sync
+                m.dma_mem_h2d_async(row, buf.ctypes.data, buf.nbytes)
+            else:
+                m.dma_mem_h2d(row, words)
+
+        def host_read(row):
+            if asynchronous:
+                buf = np.empty(N, dtype=np.uint64)
+                keep.append(buf)
+                m.dma_mem_d2h_async(buf.ctypes.data, row, buf.nbytes)
+                return buf                                # filled by the time of the final sync
+            return m.dma_mem_d2h(row, N).copy()
         for ps in range(passes):
             hw = iter(host_writes[2 * ps: 2 * ps + 2])
             if pattern == "single":
                 for pc_, (_, csr) in zip(pcs, programs):
                     m.run_vp(pc_, *csr)
                     if pc_ == pcs[0]:
-                        m.dma_mem_h2d(*next(hw))
+                        host_write(*next(hw))
             elif pattern == "multi":
                 m.run_vp(pcs[0], *programs[0][1])
-                m.dma_mem_h2d(*next(hw))
+                host_write(*next(hw))
                 m.run_vp_multi([(pcs[1], *programs[1][1]), (pcs[2], *programs[2][1])])
             else:
                 m.run_vp_batch(pcs[0], [programs[0][1], other_rows])      # the same stream over two sets of rows
-                m.dma_mem_h2d(*next(hw))
+                host_write(*next(hw))
                 m.run_vp(pcs[1], *programs[1][1])
             row, data_ = next(hw)
-            seen.append(m.dma_mem_d2h(row, N).copy())
-            m.dma_mem_h2d(row, data_)
+            seen.append(host_read(row))
+            host_write(row, data_)
+        if asynchronous:
+            m.sync()
         images.append((np.concatenate([m.dma_mem_d2h(0, SLOTS * N)] + seen), m.spm_written(0, SLOTS * N)))
     (gd, gw), (ed, ew) = images
     assert (gw == ew).all(), f"seed {seed}: written-mask differs"
