@@ -1288,7 +1288,7 @@ int aloha_create(const aloha_cfg *cfg, aloha_t **out) {
     E->nmax = nmax;
     E->kbits = ilog2(nmax);
     E->device = cfg->device;
-    E->pool_count = cfg->pool_buffers ? cfg->pool_buffers : 64;
+    E->pool_count = cfg->pool_buffers ? cfg->pool_buffers : 256;   // (two key-switch kernels' worth of temporaries per batched call, x 4)
     if (E->pool_count < 34) E->pool_count = 34;
     *out = E;   // so the caller can read last_error on failure, then destroy
     int ndev = 0;

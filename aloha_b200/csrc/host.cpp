@@ -219,17 +219,93 @@ int aloha_host_run_op_async(aloha_host_t *H, uint32_t i, uint64_t *dump, uint8_t
 // Ops [first, first + count) in one call: op first + j uses dumps + j*4n, written + j*4n, sub_dumps + j*4n,
 // sub_written + j*4n and has_sub[j].  (The per-op loop of run(), top_noaxilite_tb.sv:596-638, on this side of
 // the boundary: a caller in another language pays one FFI crossing per program, not per op.)
+//
+// PROGRAM-level scheduling.  The testbench runs one kernel per op and dumps after each; here
+// consecutive compute ops (encode_post, mul_plain, hom_add, rotate) are collected and handed to the engine as ONE
+// aloha_run_vp_multi, which levels them by their true dependencies -- the eight encode_post kernels of case2 become
+// one transform launch of sixteen jobs, four rotates share their eleven launches -- and their dumps are read back
+// after the batch.  That is the same as dumping after each op as long as nobody in the batch writes the rows another
+// member dumps, so an op joins the batch only if its dump rows are disjoint from those of every member; an encode
+// op's upload (and the dump of the raw encoder output) happens at once, ahead of the members, which is the program's
+// order as long as the members touch none of those rows.  Loads and stores close the batch.
 int aloha_host_run_range_async(aloha_host_t *H, uint32_t first, uint32_t count, uint64_t *dumps, uint8_t *written,
                                uint64_t *sub_dumps, uint8_t *sub_written, int *has_sub) {
     if (!H || (uint64_t)first + count > H->ops.size() || !dumps || !written || !sub_dumps || !sub_written || !has_sub)
         return ALOHA_E_ARG;
-    const uint64_t w = 4ull * H->n;
+    const uint64_t w = 4ull * H->n, bytes = w * 8;
+    const uint32_t ct_rows = (uint32_t)(w / kLanes), pt_rows = ct_rows / 2;
+    aloha_t *E = H->eng;
+    struct Member { uint32_t j, pc; aloha_vp_args a; uint32_t out; uint32_t src[2], src_rows[2]; };
+    std::vector<Member> batch;
+    auto apart = [](uint32_t a, uint32_t an, uint32_t b, uint32_t bn) { return a + an <= b || b + bn <= a; };
+    auto flush = [&]() -> int {
+        if (batch.empty()) return ALOHA_OK;
+        std::vector<uint32_t> pcs;
+        std::vector<aloha_vp_args> args;
+        for (const Member &m : batch) { pcs.push_back(m.pc); args.push_back(m.a); }
+        int rc = aloha_run_vp_multi(E, (uint32_t)batch.size(), pcs.data(), args.data());
+        for (size_t k = 0; k < batch.size() && !rc; ++k) {
+            const Member &m = batch[k];
+            rc = read_back_async(H, m.out, bytes, dumps + m.j * w);
+            if (!rc) rc = aloha_spm_written(E, m.out, w, written + m.j * w);
+        }
+        batch.clear();
+        return rc;
+    };
     for (uint32_t j = 0; j < count; ++j) {
-        int rc = aloha_host_run_op_async(H, first + j, dumps + j * w, written + j * w, sub_dumps + j * w, sub_written + j * w,
-                                         has_sub + j);
-        if (rc) return rc;
+        const uint32_t i = first + j;
+        const HostOp &op = H->ops[i];
+        has_sub[j] = 0;
+        Member m{j, 0, aloha_vp_args{0, 0, 0, 0, 0}, op.spm_addr, {0, 0}, {0, 0}};
+        switch (op.type) {
+        case OP_ENCODE:
+            m.pc = kPcEncodePost; m.a = aloha_vp_args{op.spm_addr, 0, op.spm_addr, 0, 0};
+            m.src[0] = op.spm_addr; m.src_rows[0] = pt_rows;
+            break;
+        case OP_MUL_PLAIN:
+            m.pc = kPcMulPlain; m.a = aloha_vp_args{op.src1, op.src2, op.spm_addr, 0, 0};
+            m.src[0] = op.src1; m.src_rows[0] = ct_rows; m.src[1] = op.src2; m.src_rows[1] = pt_rows;
+            break;
+        case OP_HOM_ADD:
+            m.pc = kPcHomAdd; m.a = aloha_vp_args{op.src1, op.src2, op.spm_addr, 0, 0};
+            m.src[0] = op.src1; m.src_rows[0] = ct_rows; m.src[1] = op.src2; m.src_rows[1] = ct_rows;
+            break;
+        case OP_ROTATE:
+            m.pc = kPcKeyswitch;
+            m.a = aloha_vp_args{op.src1, 0, op.spm_addr, (uint32_t)((clog2(op.step) - 1) * H->n * 12 / kLanes),
+                                (uint32_t)pow3_mod(op.step, 2ull * H->n)};
+            m.src[0] = op.src1; m.src_rows[0] = ct_rows;
+            break;
+        default: {                                        // load / store (or an op the single-op path rejects): in order
+            int rc = flush();
+            if (!rc) rc = aloha_host_run_op_async(H, i, dumps + j * w, written + j * w, sub_dumps + j * w, sub_written + j * w, has_sub + j);
+            if (rc) return rc;
+            continue;
+        }
+        }
+        bool joins = batch.size() < 64;
+        for (const Member &b : batch) {
+            if (!apart(m.out, ct_rows, b.out, ct_rows)) joins = false;
+            if (op.type == OP_ENCODE)                     // the upload overtakes the members: they must not read those rows
+                for (int s = 0; s < 2; ++s)
+                    if (b.src_rows[s] && !apart(m.out, pt_rows, b.src[s], b.src_rows[s])) joins = false;
+        }
+        if (!joins) {
+            int rc = flush();
+            if (rc) return rc;
+        }
+        if (op.type == OP_ENCODE) {
+            auto it = H->encoder.find(i);
+            if (it == H->encoder.end()) return ALOHA_E_STATE;
+            int rc = aloha_dma_mem_h2d(E, op.spm_addr, it->second.data(), it->second.size() * 8);
+            if (!rc) rc = read_back_async(H, op.spm_addr, bytes, sub_dumps + j * w);
+            if (!rc) rc = aloha_spm_written(E, op.spm_addr, w, sub_written + j * w);
+            if (rc) return rc;
+            has_sub[j] = 1;
+        }
+        batch.push_back(m);
     }
-    return ALOHA_OK;
+    return flush();
 }
 
 int aloha_host_run_op(aloha_host_t *H, uint32_t i, uint64_t *dump, uint8_t *written, uint64_t *sub_dump,

@@ -95,7 +95,7 @@ typedef struct aloha_cfg {
     uint32_t ksk_rows;        /* key-switch-key memory rows; reference: 9216 */
     int32_t device;           /* CUDA device ordinal */
     uint32_t flags;           /* ALOHA_F_* */
-    uint32_t pool_buffers;    /* renaming buffers of vlmax_bits/64 words (0 = 64) */
+    uint32_t pool_buffers;    /* renaming buffers of vlmax_bits/64 words (0 = 256) */
     uint64_t l2_chunk_bytes;  /* split transform launches so one chunk's footprint stays below this (0 = never split) */
     uint32_t isram_depth;     /* instruction ROM entries, IRAM_DEPTH (vp_defines.vh:31); 0 = 4096 as on the reference */
     uint32_t reserved;

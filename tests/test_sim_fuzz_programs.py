@@ -123,3 +123,48 @@ def test_random_host_programs(block):
     with sim_engine.simulated() as A:
         for seed in range(block * per, (block + 1) * per):
             run_case(A, seed)
+
+
+def test_independent_ops_share_their_launches():
+    """PROGRAM-level scheduling in the host driver: four encodes, four mul_plains and two rotates on rows of their own,
+    issued as one asynchronous range, take the launches of ONE of each (the engine levels the batch), and every dump
+    is still what the testbench would have written after each op."""
+    lines = ["10000000,00000000,00000000"]                                                  # load ct -> 0x000
+    # (encodes a whole ciphertext apart: the testbench dumps 4 polynomials after an encode, so plaintexts packed two
+    #  polynomials apart, as in the tv cases, lie inside each other's dumps and cannot share a batch)
+    lines += [f"{0x30000000 | (0x100 + 0x100 * i):08x},00000000,00000000" for i in range(4)]  # 4 encodes
+    lines += [f"{0x50000000 | (0x600 + 0x100 * i):08x},00000000,{0x100 + 0x100 * i:08x}" for i in range(4)]   # 4 mul_plains
+    lines += [f"{0x70000000 | (0xa00 + 0x100 * i):08x},{2 << i:08x},{0x600 + 0x100 * i:08x}" for i in range(2)]  # 2 rotates
+    text = "\n".join(lines)
+    ops = O.parse_program(text)
+    data = np.random.default_rng(5)
+    dram = np.zeros(64 * 1024 * 1024 // 8, dtype=np.uint64)
+    base = O.DRAM_VP_BASE // 8
+    dram[base:base + 4 * N] = data.integers(0, O.Q0, 4 * N, dtype=np.uint64)
+    enc = {i: data.integers(0, O.Q0, 2 * N, dtype=np.uint64) for i in range(1, 5)}
+    ksk = data.integers(0, O.Q0, 3 * 12 * N, dtype=np.uint64)
+    model = O.GoldenModel()
+    for words, pc in G.microcode():
+        model.load_isram(words, pc)
+    model.dma_ksk_h2d(0, ksk)
+    want = [(i, sub, d.copy(), w.copy()) for i, sub, d, w in O.replay(model, ops, dram.copy(), enc, N)]
+    with sim_engine.simulated() as A:
+        launches = {}
+        for mode in ("op by op", "range"):
+            eng = A.Engine()
+            for words, pc in G.microcode():
+                eng.load_isram(words, pc)
+            eng.dma_ksk_h2d(0, ksk)
+            host = A.HostDriver(eng, text, N)
+            for i, e in enc.items():
+                host.set_encoder_output(i, e)
+            host.dram_write(O.DRAM_VP_BASE, dram[base:base + 4 * N])
+            per_op = [host.run_op(i) for i in range(len(ops))] if mode == "op by op" else host.run_all_async()
+            got = [(i, sub, d, w) for i, dumps in enumerate(per_op) for sub, d, w in dumps]
+            assert [(i, s) for i, s, _, _ in got] == [(i, s) for i, s, _, _ in want]
+            for (i, sub, gd, gw), (_, _, wd, ww) in zip(got, want):
+                assert (np.asarray(gw, bool) == ww).all() and (gd[ww] == wd[ww]).all(), (mode, i, sub)
+            launches[mode] = eng.stats()["kernel_launches"]
+            host.close()
+            eng.close()
+    assert launches["range"] * 2 < launches["op by op"], launches
