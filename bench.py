@@ -798,7 +798,7 @@ def measure_keyswitch(torch, dist, A, eng_kwargs, stream, timed, world, rank, sh
         prm = hks.Params(N, q, p, dnum)
         lay = hks.Layout(prm, world, rank, batch)
         eng = A.Engine(vlmax_bits=N * 64, spm_rows=lay.spm_rows, ksk_rows=max(lay.ksk_rows, 1),
-                       moduli=[(m, psi[m]) for m in prm.moduli], pool_buffers=min(32768, max(2048, 4 * batch * lay.per_rank * (prm.dnum * (4 if prm.alpha > 1 else 1) + 8))),
+                       moduli=[(m, psi[m]) for m in prm.moduli], pool_buffers=min(32768, max(2048, 4 * batch * lay.per_rank * (prm.dnum * (4 if prm.alpha > 1 else 2) + 8))),
                        isram_depth=1 << 17,
                        flags=int(os.environ.get("ALOHA_BENCH_KS_FLAGS", "0")), **eng_kwargs)
         eng.set_stream(stream.cuda_stream)
